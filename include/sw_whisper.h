@@ -1,0 +1,172 @@
+/*
+ * sw_whisper.h - C ABI of the B200-native Whisper inference hot path.
+ *
+ * This is the drop-in boundary for the path the reference reaches through the
+ * whisper.cpp C API from exactly one file, src/stt_engine.cpp.
+ * Each entry point names the reference interface it replaces (file:line in
+ * /root/reference). Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions: functions returning int return 0 on success and a negative
+ * value on failure; sw_last_error() then holds a thread-local message. No
+ * exceptions cross this boundary. Handles are opaque. A sw_ctx may be shared by
+ * threads; results are owned by the caller until sw_result_free().
+ *
+ * There is NO CPU fallback behind this ABI: every compute entry point fails
+ * loudly (negative return + message) when no sm_100 device is present.
+ */
+#ifndef SW_WHISPER_H
+#define SW_WHISPER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SW_API __attribute__((visibility("default")))
+
+typedef struct sw_ctx sw_ctx;
+typedef struct sw_result sw_result;
+
+/* ---- library ---------------------------------------------------------- */
+SW_API const char* sw_last_error(void);
+SW_API const char* sw_version(void);
+/* number of CUDA devices with compute capability 10.x; 0 if none / no driver */
+SW_API int sw_device_count(void);
+
+/* replaces whisper_log_set (main.cpp:71); level: 2=info 3=warn 4=error, the
+ * ggml_log_level values the reference's bridge switches on (main.cpp:37-55) */
+typedef void (*sw_log_callback)(int level, const char* text, void* user);
+SW_API void sw_log_set(sw_log_callback cb, void* user);
+
+/* ---- context lifecycle ------------------------------------------------ */
+/* replaces whisper_context_default_params (stt_engine.cpp:28) */
+typedef struct sw_ctx_params {
+  int device;          /* CUDA ordinal */
+  int max_batch;       /* windows decoded together (default 64) */
+  int max_beams;       /* decoders per window (default 5) */
+  int flash_attn;      /* accepted for API compatibility; always fused */
+  int reserved[12];
+} sw_ctx_params;
+SW_API sw_ctx_params sw_ctx_default_params(void);
+
+/* replaces whisper_init_from_file_with_params + whisper_init_state
+ * (stt_engine.cpp:33,39): parses the legacy ggml .bin, uploads weights to HBM
+ * as bf16, allocates KV caches / activations for max_batch windows.
+ * Returns NULL on failure. */
+SW_API sw_ctx* sw_ctx_create(const char* ggml_model_path, const sw_ctx_params* params);
+/* replaces whisper_free_state + whisper_free (stt_engine.cpp:56-57) */
+SW_API void sw_ctx_destroy(sw_ctx* ctx);
+
+/* model facts (whisper_model_* / whisper_n_* accessors upstream) */
+typedef struct sw_model_info {
+  int n_vocab, n_audio_ctx, n_audio_state, n_audio_head, n_audio_layer;
+  int n_text_ctx, n_text_state, n_text_head, n_text_layer, n_mels, ftype;
+  int is_multilingual;
+  int token_eot, token_sot, token_translate, token_transcribe, token_solm;
+  int token_prev, token_nosp, token_not, token_beg;
+} sw_model_info;
+SW_API int sw_ctx_model_info(const sw_ctx* ctx, sw_model_info* out);
+/* replaces whisper_token_to_str (stt_engine.cpp:291); borrowed pointer */
+SW_API const char* sw_token_to_str(const sw_ctx* ctx, int token);
+/* replaces whisper_token_eot (stt_engine.cpp:292) */
+SW_API int sw_token_eot(const sw_ctx* ctx);
+/* whisper_lang_id upstream: "en" -> 0 ...; -1 if unknown */
+SW_API int sw_lang_id(const char* lang);
+
+/* ---- decode parameters ------------------------------------------------ */
+/* replaces whisper_full_params as filled at stt_engine.cpp:204-243 */
+typedef int (*sw_abort_callback)(void* user); /* nonzero = abort (stt_engine.cpp:17-23) */
+typedef struct sw_full_params {
+  int strategy;            /* 0 greedy, 1 beam search (stt_engine.cpp:210-212) */
+  int beam_size;           /* stt_engine.cpp:236 */
+  int best_of;             /* stt_engine.cpp:238 */
+  float temperature;       /* stt_engine.cpp:234 */
+  float temperature_inc;   /* upstream default 0.2; 0 disables fallback */
+  float entropy_thold;     /* stt_engine.cpp:241 */
+  float logprob_thold;     /* stt_engine.cpp:242 */
+  float no_speech_thold;   /* stt_engine.cpp:227 */
+  int translate;           /* stt_engine.cpp:228 */
+  int tdrz_enable;         /* stt_engine.cpp:229 */
+  int suppress_nst;        /* stt_engine.cpp:226 */
+  int suppress_blank;      /* upstream default 1 */
+  int token_timestamps;    /* stt_engine.cpp:225 */
+  int no_timestamps;       /* upstream default 0 */
+  int single_segment;      /* upstream default 0 */
+  int no_context;          /* upstream default 1 */
+  float max_initial_ts;    /* upstream default 1.0 */
+  float length_penalty;    /* upstream default -1 */
+  const char* language;    /* stt_engine.cpp:232; "auto" or NULL = detect */
+  const char* initial_prompt; /* stt_engine.cpp:233 */
+  const int32_t* prompt_tokens; /* pre-tokenised prompt (upstream field of the same name) */
+  int prompt_n_tokens;
+  sw_abort_callback abort_callback;    /* stt_engine.cpp:217 */
+  void* abort_callback_user_data;      /* stt_engine.cpp:218 */
+  int n_threads;           /* stt_engine.cpp:243; host sequencer threads */
+  int reserved[8];
+} sw_full_params;
+/* replaces whisper_full_default_params (stt_engine.cpp:214) */
+SW_API sw_full_params sw_full_default_params(int strategy);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* replaces whisper_full_with_state (stt_engine.cpp:245-246) for ONE utterance
+ * of 16 kHz mono float PCM in host memory. *out receives the result. Returns 0
+ * ok, non-zero on failure or abort (upstream convention). */
+SW_API int sw_full(sw_ctx* ctx, const sw_full_params* params, const float* pcm, int n_samples,
+                   sw_result** out);
+/* int16 entry: folds the reference's host-side /32768 conversion loop
+ * (transcribe_pcm16, stt_engine.cpp:117-125) into the device front end. */
+SW_API int sw_full_pcm16(sw_ctx* ctx, const sw_full_params* params, const int16_t* pcm,
+                         int n_samples, sw_result** out);
+/* Batched entry the reference lacks (it runs one whisper_state per request,
+ * stt_engine.cpp:36-42): n utterances decoded together. pcm16[i] points at
+ * n_samples[i] int16 host samples. out[i] receives one result per utterance. */
+SW_API int sw_full_batch_pcm16(sw_ctx* ctx, const sw_full_params* params,
+                               const int16_t* const* pcm16, const int* n_samples, int n,
+                               sw_result** out);
+
+/* ---- result accessors (whisper_full_*_from_state, stt_engine.cpp:261-292) */
+typedef struct sw_token_data { /* whisper_token_data */
+  int32_t id, tid;
+  float p, plog, pt, ptsum;
+  int64_t t0, t1, t_dtw;
+  float vlen;
+} sw_token_data;
+SW_API int sw_result_n_segments(const sw_result* r);                       /* :261 */
+SW_API const char* sw_result_segment_text(const sw_result* r, int i);      /* :267 */
+SW_API int64_t sw_result_segment_t0(const sw_result* r, int i);            /* :280 */
+SW_API int64_t sw_result_segment_t1(const sw_result* r, int i);            /* :281 */
+SW_API int sw_result_segment_speaker_turn_next(const sw_result* r, int i); /* :283 */
+SW_API int sw_result_n_tokens(const sw_result* r, int i);                  /* :286 */
+SW_API sw_token_data sw_result_token_data(const sw_result* r, int i, int j); /* :290 */
+SW_API int sw_result_lang_id(const sw_result* r);
+/* decode-loop statistics for the benchmark */
+SW_API int sw_result_n_decode_steps(const sw_result* r);
+SW_API void sw_result_free(sw_result* r);
+
+/* ---- stage-level hooks (parity tests and roofline measurement) --------- *
+ * Host pointers in, host pointers out, synchronous. */
+/* log-mel of one utterance (whisper.cpp log_mel_spectrogram): out is
+ * [n_mel][n_len] f32 mel-major; returns n_len via *n_len. Pass out=NULL to
+ * query n_len only. */
+SW_API int sw_mel_pcm16(sw_ctx* ctx, const int16_t* pcm, int n_samples, float* out, int* n_len);
+SW_API int sw_mel_f32(sw_ctx* ctx, const float* pcm, int n_samples, float* out, int* n_len);
+/* encoder over n_windows windows of mel [n_windows][n_mel][3000] f32;
+ * out [n_windows][1500][d] f32 (post ln_post). */
+SW_API int sw_encode(sw_ctx* ctx, const float* mel, int n_windows, float* out);
+/* teacher-forced decoder: tokens [n_windows][n_tok]; returns raw logits
+ * [n_windows][n_tok][n_vocab] f32 for the windows last passed to sw_encode. */
+SW_API int sw_decode_logits(sw_ctx* ctx, const int32_t* tokens, int n_windows, int n_tok,
+                            float* logits);
+
+/* ---- device-pointer kernel hooks (tests/bench; pointers are DEVICE) ---- */
+/* C[M,N] = epi(A[M,K] . B[N,K]^T), bf16 in, flags: 1 gelu, 2 f32 out, 4 row bias */
+SW_API int sw_dev_gemm_bf16(const void* dA, const void* dB, void* dC, const float* d_bias,
+                            const float* d_residual, int M, int N, int K, int lda, int ldb, int ldc,
+                            int flags, int block_n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SW_WHISPER_H */

@@ -1,0 +1,399 @@
+// bf16 x bf16 -> f32 GEMM for sm_100a: TMA -> 128B-swizzled smem ring ->
+// tcgen05.mma (accumulators in TMEM, double buffered) -> tcgen05.ld epilogue.
+//
+// Persistent, warp specialised, one CTA per SM:
+//   warp 0      : TMA producer (one elected lane)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane)
+//   warps 2..5  : epilogue; warp w drains TMEM lanes [32*(w%4), 32*(w%4)+32)
+//
+// This is the kernel behind every dense contraction of the Whisper path the
+// reference runs through ggml's mul_mat: conv stem (implicit
+// GEMM through strided TMA maps), encoder QKV/out/MLP projections, cross-KV
+// projection and the decoder's prompt/logit projections
+// (call site in the reference: whisper_full_with_state, stt_engine.cpp:245).
+#include "common.cuh"
+#include "gemm.cuh"
+
+#include <mutex>
+
+namespace sw {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+constexpr int SMEM_BUDGET = 227 * 1024;
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - 2048) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered accumulator
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct EpiParams {
+  void* C;
+  int64_t ldc, c_batch_stride;
+  const float* bias;
+  const float* residual;
+  int64_t ldr, r_batch_stride;
+  int res_mod;
+  int flags;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
+                    const __grid_constant__ CUtensorMap map_b, EpiParams epi, int M, int N, int K,
+                    int batch, int b_batched) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024-byte aligned tiles.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  const int total_tiles = m_tiles * n_tiles * batch;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc(tmem_base_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % n_tiles;
+        const int m_blk = (tile / n_tiles) % m_tiles;
+        const int b = tile / (n_tiles * m_tiles);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          tma_load_3d(sa, &map_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M, b);
+          tma_load_3d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N,
+                      b_batched ? b : 0);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t adesc = make_umma_desc_sw128(sa);
+          const uint64_t bdesc = make_umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 B (16 bf16) inside the 128B swizzle row: +2 in the
+            // (addr >> 4) start-address field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp_idx & 3;  // TMEM lane quarter this warp may touch
+    const bool out_f32 = (epi.flags & GEMM_OUT_F32) != 0;
+    const bool do_gelu = (epi.flags & GEMM_GELU) != 0;
+    const bool bias_row = (epi.flags & GEMM_BIAS_ROW) != 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_blk = tile % n_tiles;
+      const int m_blk = (tile / n_tiles) % m_tiles;
+      const int b = tile / (n_tiles * m_tiles);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+
+      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < M;
+      const int64_t rrow = epi.res_mod > 0 ? (row % epi.res_mod) : row;
+      const float* rptr =
+          epi.residual ? epi.residual + b * epi.r_batch_stride + rrow * epi.ldr : nullptr;
+      const float row_bias = (bias_row && epi.bias && row_ok) ? epi.bias[row] : 0.0f;
+
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (col0 >= N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + acc * BLOCK_N + c * 32 + (static_cast<uint32_t>(q * 32) << 16),
+                           r);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const bool full = (col0 + 32 <= N);
+        if (epi.bias) {
+          if (bias_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += row_bias;
+          } else if (full) {
+            const float4* bp = reinterpret_cast<const float4*>(epi.bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 t = __ldg(bp + j);
+              v[4 * j + 0] += t.x;
+              v[4 * j + 1] += t.y;
+              v[4 * j + 2] += t.z;
+              v[4 * j + 3] += t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) v[j] += epi.bias[col0 + j];
+          }
+        }
+        if (do_gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+        }
+        if (rptr) {
+          if (full) {
+            const float4* rp = reinterpret_cast<const float4*>(rptr + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 t = rp[j];
+              v[4 * j + 0] += t.x;
+              v[4 * j + 1] += t.y;
+              v[4 * j + 2] += t.z;
+              v[4 * j + 3] += t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) v[j] += rptr[col0 + j];
+          }
+        }
+        if (out_f32) {
+          float* cp = static_cast<float*>(epi.C) + b * epi.c_batch_stride + (int64_t)row * epi.ldc + col0;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(cp)[j] =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) cp[j] = v[j];
+          }
+        } else {
+          __nv_bfloat16* cp = static_cast<__nv_bfloat16*>(epi.C) + b * epi.c_batch_stride +
+                              (int64_t)row * epi.ldc + col0;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              reinterpret_cast<uint4*>(cp)[j] = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) cp[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+      // hand the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 3-D bf16 K-major operand map: dims {K, rows, batch}, box {64, box_rows, 1}, 128B swizzle.
+int make_operand_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows, int64_t batch,
+                     int64_t ld_elems, int64_t batch_stride_elems, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  SW_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  SW_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "GEMM operand base not 16B aligned");
+  SW_CHECK((ld_elems * 2) % 16 == 0, "GEMM operand row stride %lld not a multiple of 8 elements",
+           (long long)ld_elems);
+  if (batch <= 1 || batch_stride_elems == 0) {
+    batch = 1;
+    batch_stride_elems = rows * ld_elems;
+  }
+  SW_CHECK((batch_stride_elems * 2) % 16 == 0, "GEMM batch stride not 16B aligned");
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld_elems * 2, (cuuint64_t)batch_stride_elems * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SW_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: %d (K=%lld rows=%lld ld=%lld)", (int)r,
+           (long long)K, (long long)rows, (long long)ld_elems);
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BLOCK_N>
+int launch(const GemmArgs& a, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SW_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap map_a, map_b;
+  if (make_operand_map(&map_a, a.A, a.K, a.M, a.batch, a.lda, a.a_batch_stride, BLOCK_M)) return -1;
+  const bool b_batched = a.b_batch_stride != 0 && a.batch > 1;
+  if (make_operand_map(&map_b, a.B, a.K, a.N, b_batched ? a.batch : 1, a.ldb, a.b_batch_stride,
+                       BLOCK_N))
+    return -1;
+  EpiParams epi;
+  epi.C = a.C;
+  epi.ldc = a.ldc;
+  epi.c_batch_stride = a.c_batch_stride;
+  epi.bias = a.bias;
+  epi.residual = a.residual;
+  epi.ldr = a.ldr;
+  epi.r_batch_stride = a.r_batch_stride;
+  epi.res_mod = a.res_mod;
+  epi.flags = a.flags;
+  const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
+  const int64_t tiles = (int64_t)m_tiles * n_tiles * a.batch;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  gemm_tcgen05_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(
+      map_a, map_b, epi, a.M, a.N, a.K, a.batch, b_batched ? 1 : 0);
+  SW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
+  SW_CHECK(a.M > 0 && a.N > 0 && a.K > 0 && a.batch > 0, "gemm: empty problem");
+  SW_CHECK(a.A && a.B && a.C, "gemm: null operand");
+  const bool out_f32 = (a.flags & GEMM_OUT_F32) != 0;
+  SW_CHECK(a.ldc % (out_f32 ? 4 : 8) == 0, "gemm: ldc %lld breaks 16B store alignment",
+           (long long)a.ldc);
+  SW_CHECK((reinterpret_cast<uintptr_t>(a.C) & 15) == 0, "gemm: C not 16B aligned");
+  if (a.residual) SW_CHECK(a.ldr % 4 == 0, "gemm: ldr must be a multiple of 4");
+  int bn = a.block_n;
+  if (bn == 0) {
+    // Largest tile that still gives every SM work; small problems prefer more tiles.
+    const int64_t m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+    bn = 256;
+    while (bn > 64 && (m_tiles * ((a.N + bn - 1) / bn) * a.batch < num_sms() || a.N <= bn / 2))
+      bn >>= 1;
+  }
+  switch (bn) {
+    case 64: return launch<64>(a, stream);
+    case 128: return launch<128>(a, stream);
+    case 256: return launch<256>(a, stream);
+    default: set_last_error("gemm: unsupported block_n %d", bn); return -1;
+  }
+}
+
+}  // namespace sw

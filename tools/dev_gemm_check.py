@@ -18,13 +18,16 @@ def run(M, N, K, flags=0, bias=False, res=False, block_n=0, seed=0):
     A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
     B = (torch.randn(N, K, device="cuda", generator=g) * 0.5).bfloat16()
     out_f32 = bool(flags & 2)
-    C = torch.full((M, N), 7.0, device="cuda", dtype=torch.float32 if out_f32 else torch.bfloat16)
+    ldc = (N + 7) // 8 * 8
+    Cfull = torch.full((M, ldc), 7.0, device="cuda", dtype=torch.float32 if out_f32 else torch.bfloat16)
+    C = Cfull[:, :N]
     bias_t = torch.randn(M if flags & 4 else N, device="cuda", generator=g) if bias else None
-    res_t = torch.randn(M, N, device="cuda", generator=g) if res else None
-    rc = lib.sw_dev_gemm_bf16(A.data_ptr(), B.data_ptr(), C.data_ptr(),
+    res_full = torch.randn(M, ldc, device="cuda", generator=g) if res else None
+    res_t = res_full[:, :N] if res else None
+    rc = lib.sw_dev_gemm_bf16(A.data_ptr(), B.data_ptr(), Cfull.data_ptr(),
                               bias_t.data_ptr() if bias else None,
-                              res_t.data_ptr() if res else None,
-                              M, N, K, K, K, N, flags, block_n, None)
+                              res_full.data_ptr() if res else None,
+                              M, N, K, K, K, ldc, flags, block_n, None)
     if rc != 0:
         return dict(M=M, N=N, K=K, flags=flags, ok=False, err=lib.sw_last_error().decode())
     torch.cuda.synchronize()
@@ -84,7 +87,7 @@ if __name__ == "__main__":
         (1500, 384, 1536, 2, True, True, 0),
         (3000, 1280, 384, 1, True, False, 0),
         (777, 200, 136, 2, True, True, 0),      # ragged M/N/K tails
-        (5000, 51866 // 2 * 2, 384, 2, False, False, 256),
+        (5000, 51866, 384, 2, False, False, 256),
         (96000, 1280, 1280, 0, True, False, 256),
         (4096, 4096, 4096, 2, False, False, 256),
         (1000, 640, 512, 6, True, False, 0),    # row bias

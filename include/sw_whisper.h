@@ -125,6 +125,11 @@ SW_API int sw_full_pcm16(sw_ctx* ctx, const sw_full_params* params, const int16_
 SW_API int sw_full_batch_pcm16(sw_ctx* ctx, const sw_full_params* params,
                                const int16_t* const* pcm16, const int* n_samples, int n,
                                sw_result** out);
+SW_API int sw_full_batch_f32(sw_ctx* ctx, const sw_full_params* params, const float* const* pcm,
+                             const int* n_samples, int n, sw_result** out);
+/* page-locked host memory for PCM staging (optional; any host pointer is accepted) */
+SW_API void* sw_host_alloc(size_t bytes);
+SW_API void sw_host_free(void* p);
 
 /* ---- result accessors (whisper_full_*_from_state, stt_engine.cpp:261-292) */
 typedef struct sw_token_data { /* whisper_token_data */
@@ -143,7 +148,17 @@ SW_API sw_token_data sw_result_token_data(const sw_result* r, int i, int j); /* 
 SW_API int sw_result_lang_id(const sw_result* r);
 /* decode-loop statistics for the benchmark */
 SW_API int sw_result_n_decode_steps(const sw_result* r);
+SW_API int sw_result_n_windows(const sw_result* r);
 SW_API void sw_result_free(sw_result* r);
+
+/* ---- per-context device-time statistics (CUDA events on the engine's stream) ---- */
+typedef struct sw_stats {
+  double ms_mel, ms_encode, ms_decode; /* accumulated device time per stage */
+  long n_windows, n_steps, n_launches; /* windows encoded, decoder steps, kernels launched */
+  double decode_bytes;                 /* algorithmic bytes of the sampled decode steps */
+  double decoder_weight_bytes;         /* bytes of decoder weights one step streams */
+} sw_stats;
+SW_API int sw_ctx_get_stats(sw_ctx* ctx, sw_stats* out, int reset);
 
 /* ---- stage-level hooks (parity tests and roofline measurement) --------- *
  * Host pointers in, host pointers out, synchronous. */

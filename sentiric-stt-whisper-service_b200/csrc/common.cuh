@@ -9,30 +9,9 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include "host_common.h"
+
 namespace sw {
-
-// ----------------------------------------------------------------------------
-// error handling (host)
-// ----------------------------------------------------------------------------
-void set_last_error(const char* fmt, ...);
-
-#define SW_CUDA_CHECK(expr)                                                       \
-  do {                                                                            \
-    cudaError_t _e = (expr);                                                      \
-    if (_e != cudaSuccess) {                                                      \
-      ::sw::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,          \
-                           cudaGetErrorString(_e));                               \
-      return -1;                                                                  \
-    }                                                                             \
-  } while (0)
-
-#define SW_CHECK(cond, ...)                                                       \
-  do {                                                                            \
-    if (!(cond)) {                                                                \
-      ::sw::set_last_error(__VA_ARGS__);                                          \
-      return -1;                                                                  \
-    }                                                                             \
-  } while (0)
 
 // ----------------------------------------------------------------------------
 // small device helpers

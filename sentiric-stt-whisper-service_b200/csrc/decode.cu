@@ -1,0 +1,655 @@
+// Per-token decoder kernels: paged self-KV append + causal self attention, the cross attention
+// that streams each window's cross-KV exactly once per step, and the logit rules / log-softmax /
+// argmax-or-draw kernel. Together they replace, for one batched step, the device part of
+// whisper_decode_internal and the CPU whisper_process_logits / whisper_sample_token* of
+// whisper.cpp (reference call site stt_engine.cpp:245).
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace sw {
+namespace {
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
+__device__ __forceinline__ const bf16* page_ptr(const bf16* pool, const int* page_table, int slot,
+                                                int pos, int layer, int n_layer, int kv, int d) {
+  const int page = page_table[slot * KV_MAX_PAGES + pos / KV_PAGE];
+  return pool + ((((int64_t)page * n_layer + layer) * 2 + kv) * KV_PAGE + (pos % KV_PAGE)) * d;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void kv_append_kernel(const bf16* __restrict__ qkv, const DecRow* __restrict__ rows, int d,
+                                 bf16* __restrict__ pool, const int* __restrict__ page_table, int layer,
+                                 int n_layer) {
+  const DecRow r = rows[blockIdx.x];
+  const uint4* src = reinterpret_cast<const uint4*>(qkv + (int64_t)blockIdx.x * 3 * d + d);
+  uint4* dk = reinterpret_cast<uint4*>(const_cast<bf16*>(page_ptr(pool, page_table, r.slot, r.pos, layer, n_layer, 0, d)));
+  uint4* dv = reinterpret_cast<uint4*>(const_cast<bf16*>(page_ptr(pool, page_table, r.slot, r.pos, layer, n_layer, 1, d)));
+  const int nv = d / 8;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    dk[i] = src[i];
+    dv[i] = src[nv + i];
+  }
+}
+
+__global__ void kv_copy_pages_kernel(bf16* __restrict__ pool, const int* __restrict__ pairs, int64_t page_elems) {
+  const int src = pairs[2 * blockIdx.y], dst = pairs[2 * blockIdx.y + 1];
+  const uint4* s = reinterpret_cast<const uint4*>(pool + (int64_t)src * page_elems);
+  uint4* d = reinterpret_cast<uint4*>(pool + (int64_t)dst * page_elems);
+  const int64_t nv = page_elems / 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = s[i];
+}
+
+// one CTA (128 threads) per (row, head); n_kv = pos + 1 <= 448
+__global__ void __launch_bounds__(128)
+self_attention_kernel(const bf16* __restrict__ qkv, const DecRow* __restrict__ rows, int d,
+                      const bf16* __restrict__ pool, const int* __restrict__ page_table, int layer,
+                      int n_layer, bf16* __restrict__ out) {
+  __shared__ float qs[64];
+  __shared__ float sc[448];
+  __shared__ float red[4];
+  __shared__ float part[4][64];
+  const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const DecRow row = rows[r];
+  const int n_kv = row.pos + 1;
+  if (tid < 64) qs[tid] = __bfloat162float(qkv[(int64_t)r * 3 * d + h * 64 + tid]) * 0.125f;
+  __syncthreads();
+  float lmax = -INFINITY;
+  for (int k = tid; k < n_kv; k += 128) {
+    const uint4* kp = reinterpret_cast<const uint4*>(page_ptr(pool, page_table, row.slot, k, layer, n_layer, 0, d) + h * 64);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float f[8];
+      bf16x8_to_f32(kp[c], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc += qs[c * 8 + e] * f[e];
+    }
+    sc[k] = acc;
+    lmax = fmaxf(lmax, acc);
+  }
+  lmax = warp_max(lmax);
+  if ((tid & 31) == 0) red[tid >> 5] = lmax;
+  __syncthreads();
+  const float mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float lsum = 0.f;
+  for (int k = tid; k < n_kv; k += 128) {
+    const float p = __expf(sc[k] - mx);
+    sc[k] = p;
+    lsum += p;
+  }
+  lsum = warp_sum(lsum);
+  if ((tid & 31) == 0) red[tid >> 5] = lsum;
+  __syncthreads();
+  const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
+  // P.V: warp w takes keys w, w+4, ...; lane owns dims 2*lane, 2*lane+1
+  const int w = tid >> 5, lane = tid & 31;
+  float a0 = 0.f, a1 = 0.f;
+  for (int k = w; k < n_kv; k += 4) {
+    const bf16* vp = page_ptr(pool, page_table, row.slot, k, layer, n_layer, 1, d) + h * 64;
+    const uint32_t u = reinterpret_cast<const uint32_t*>(vp)[lane];
+    const float p = sc[k];
+    a0 += p * __uint_as_float(u << 16);
+    a1 += p * __uint_as_float(u & 0xffff0000u);
+  }
+  part[w][2 * lane] = a0;
+  part[w][2 * lane + 1] = a1;
+  __syncthreads();
+  if (tid < 64) {
+    const float v = (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]) * inv;
+    out[(int64_t)r * d + h * 64 + tid] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cross attention. CTA = (group g = one window and its <= 8 decoder rows, chunk of keys).
+// Warp 8 is the producer: 1-D bulk copies (cp.async.bulk) of 16-key slabs [K row | V row] into a
+// smem ring, completion on mbarriers. Warps 0..7 consume: warp cw serves decoder cw % cnt and key
+// split cw / cnt, so the slab is read from HBM once however many beams share the window.
+// Lane layout: a row of d bf16 is d/8 16-byte chunks; lane owns chunk it*32+lane (8 lanes / head).
+// ------------------------------------------------------------------------------------------
+constexpr int XA_KEYS = 16;
+constexpr int XA_CONSUMERS = 8;
+constexpr int XA_THREADS = (XA_CONSUMERS + 1) * 32;
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int NITER>
+__global__ void __launch_bounds__(XA_THREADS, 1)
+cross_attention_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv,
+                       const int* __restrict__ grp_win, const int* __restrict__ grp_start,
+                       const int* __restrict__ grp_count, int T, int d, int n_head,
+                       int stages_per_chunk, int n_stages, int n_chunks, float* __restrict__ ws) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int stage_bytes = XA_KEYS * 2 * d * 2;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * stage_bytes);
+  uint64_t* empty = full + n_stages;
+
+  const int g = blockIdx.y, chunk = blockIdx.x;
+  const int win = grp_win[g], r0 = grp_start[g], cnt = grp_count[g];
+  const int key_begin = chunk * stages_per_chunk * XA_KEYS;
+  const int key_end = min(T, key_begin + stages_per_chunk * XA_KEYS);
+  const int n_st = (key_end - key_begin + XA_KEYS - 1) / XA_KEYS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks_per_row = d >> 3;
+  const int row_f = d + 2 * n_head;  // floats per (row, chunk) partial
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], XA_CONSUMERS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == XA_CONSUMERS) {
+    if (lane == 0) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(kv + ((int64_t)win * T + key_begin) * 2 * d);
+      for (int i = 0; i < n_st; ++i) {
+        const int s = i % n_stages;
+        const uint32_t ph = (i / n_stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int nk = min(XA_KEYS, key_end - key_begin - i * XA_KEYS);
+        const uint32_t bytes = (uint32_t)nk * 2 * d * 2;
+        mbar_arrive_expect_tx(&full[s], bytes);
+        bulk_g2s(smem + (size_t)s * stage_bytes, src + (size_t)i * stage_bytes, bytes, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers
+  const int KS = XA_CONSUMERS / cnt;  // key splits per decoder
+  const int dd = warp % cnt, ks = warp / cnt;
+  const bool active = ks < KS;
+  float qf[NITER][8], acc[NITER][8], m[NITER], l[NITER];
+#pragma unroll
+  for (int it = 0; it < NITER; ++it) {
+    m[it] = -INFINITY;
+    l[it] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[it][e] = 0.f, qf[it][e] = 0.f;
+  }
+  if (active) {
+    const float qs = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) {
+      const int c = it * 32 + lane;
+      if (c < chunks_per_row) {
+        const uint4 u = reinterpret_cast<const uint4*>(q + (int64_t)(r0 + dd) * d)[c];
+        bf16x8_to_f32(u, qf[it]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qf[it][e] *= qs;
+      }
+    }
+  }
+  for (int i = 0; i < n_st; ++i) {
+    const int s = i % n_stages;
+    const uint32_t ph = (i / n_stages) & 1;
+    mbar_wait(&full[s], ph);
+    if (active) {
+      const uint8_t* sb = smem + (size_t)s * stage_bytes;
+      const int nk = min(XA_KEYS, key_end - key_begin - i * XA_KEYS);
+      for (int kk = ks; kk < nk; kk += KS) {
+        const uint4* kr = reinterpret_cast<const uint4*>(sb + (size_t)kk * 4 * d);
+        const uint4* vr = kr + chunks_per_row;
+#pragma unroll
+        for (int it = 0; it < NITER; ++it) {
+          const int c = it * 32 + lane;
+          const bool ok = c < chunks_per_row;
+          float kf[8], vf[8];
+          const uint4 ku = ok ? kr[c] : make_uint4(0, 0, 0, 0);
+          const uint4 vu = ok ? vr[c] : make_uint4(0, 0, 0, 0);
+          bf16x8_to_f32(ku, kf);
+          bf16x8_to_f32(vu, vf);
+          float sdot = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sdot += qf[it][e] * kf[e];
+          sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+          sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+          sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+          const float mn = fmaxf(m[it], sdot);
+          const float alpha = fast_exp2(m[it] - mn);
+          const float p = fast_exp2(sdot - mn);
+          m[it] = mn;
+          l[it] = l[it] * alpha + p;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[it][e] = acc[it][e] * alpha + p * vf[e];
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  // ---- merge the key splits of each decoder through smem (ring is drained by now)
+  asm volatile("bar.sync 1, %0;" ::"n"(XA_CONSUMERS * 32));
+  float* mg = reinterpret_cast<float*>(smem);  // [warp][it][lane][10]
+  if (active && ks > 0) {
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) {
+      float* p = mg + ((warp * NITER + it) * 32 + lane) * 10;
+      p[0] = m[it];
+      p[1] = l[it];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) p[2 + e] = acc[it][e];
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(XA_CONSUMERS * 32));
+  if (active && ks == 0) {
+    for (int k2 = 1; k2 < KS; ++k2) {
+      const int ow = dd + cnt * k2;
+#pragma unroll
+      for (int it = 0; it < NITER; ++it) {
+        const float* p = mg + ((ow * NITER + it) * 32 + lane) * 10;
+        const float m2 = p[0], l2 = p[1];
+        const float mn = fmaxf(m[it], m2);
+        const float a1 = (m[it] == -INFINITY) ? 0.f : fast_exp2(m[it] - mn);
+        const float a2 = (m2 == -INFINITY) ? 0.f : fast_exp2(m2 - mn);
+        l[it] = l[it] * a1 + l2 * a2;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[it][e] = acc[it][e] * a1 + p[2 + e] * a2;
+        m[it] = mn;
+      }
+    }
+    float* o = ws + ((int64_t)(r0 + dd) * n_chunks + chunk) * row_f;
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) {
+      const int c = it * 32 + lane;
+      if (c < chunks_per_row) {
+        reinterpret_cast<float4*>(o + c * 8)[0] = make_float4(acc[it][0], acc[it][1], acc[it][2], acc[it][3]);
+        reinterpret_cast<float4*>(o + c * 8)[1] = make_float4(acc[it][4], acc[it][5], acc[it][6], acc[it][7]);
+        if ((lane & 7) == 0) {
+          o[d + (c >> 3)] = m[it];
+          o[d + n_head + (c >> 3)] = l[it];
+        }
+      }
+    }
+  }
+}
+
+__global__ void cross_combine_kernel(const float* __restrict__ ws, int n_chunks, int d, int n_head,
+                                     bf16* __restrict__ out) {
+  const int r = blockIdx.x;
+  const int row_f = d + 2 * n_head;
+  for (int c = threadIdx.x; c < (d >> 3); c += blockDim.x) {
+    const int h = c >> 3;
+    const float* base = ws + (int64_t)r * n_chunks * row_f;
+    float M = -INFINITY;
+    for (int k = 0; k < n_chunks; ++k) M = fmaxf(M, base[(int64_t)k * row_f + d + h]);
+    float L = 0.f, a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = 0.f;
+    for (int k = 0; k < n_chunks; ++k) {
+      const float* p = base + (int64_t)k * row_f;
+      const float mk = p[d + h];
+      const float wgt = (mk == -INFINITY) ? 0.f : fast_exp2(mk - M);
+      L += p[d + n_head + h] * wgt;
+      const float4 x0 = reinterpret_cast<const float4*>(p + c * 8)[0];
+      const float4 x1 = reinterpret_cast<const float4*>(p + c * 8)[1];
+      a[0] += x0.x * wgt; a[1] += x0.y * wgt; a[2] += x0.z * wgt; a[3] += x0.w * wgt;
+      a[4] += x1.x * wgt; a[5] += x1.y * wgt; a[6] += x1.z * wgt; a[7] += x1.w * wgt;
+    }
+    const float inv = 1.0f / L;
+    uint4 o;
+    o.x = pack_bf16x2(a[0] * inv, a[1] * inv);
+    o.y = pack_bf16x2(a[2] * inv, a[3] * inv);
+    o.z = pack_bf16x2(a[4] * inv, a[5] * inv);
+    o.w = pack_bf16x2(a[6] * inv, a[7] * inv);
+    reinterpret_cast<uint4*>(out + (int64_t)r * d)[c] = o;
+  }
+}
+
+int xa_plan(int n_groups, int T, int d, int* stages_per_chunk, int* n_chunks, int* n_stages) {
+  const int total_stages = (T + XA_KEYS - 1) / XA_KEYS;
+  int sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // aim for >= 2 waves of CTAs over the SMs, at least 4 stages per chunk
+  int want_chunks = (2 * sms + n_groups - 1) / n_groups;
+  if (want_chunks < 1) want_chunks = 1;
+  int spc = (total_stages + want_chunks - 1) / want_chunks;
+  if (spc < 4) spc = 4;
+  if (spc > total_stages) spc = total_stages;
+  *stages_per_chunk = spc;
+  *n_chunks = (total_stages + spc - 1) / spc;
+  const int stage_bytes = XA_KEYS * 2 * d * 2;
+  int ns = (200 * 1024) / stage_bytes;
+  if (ns > 6) ns = 6;
+  if (ns < 2) ns = 2;
+  *n_stages = ns;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// logits: rules -> log-softmax -> timestamp-vs-text -> argmax or inverse-CDF draws
+// ------------------------------------------------------------------------------------------
+constexpr int LP_THREADS = 1024;
+
+struct ArgMax {
+  float v;
+  int i;
+};
+__device__ __forceinline__ ArgMax am_better(ArgMax a, ArgMax b) {  // larger v, then smaller index
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+__device__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < LP_THREADS / 32; ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+__device__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < LP_THREADS / 32; ++i) r += red[i];
+  return r;
+}
+__device__ double block_sum_d(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < LP_THREADS / 32; ++i) r += red[i];
+  return r;
+}
+__device__ ArgMax block_argmax(ArgMax a, float* redv, int* redi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax b;
+    b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
+    b.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    a = am_better(a, b);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    redv[threadIdx.x >> 5] = a.v;
+    redi[threadIdx.x >> 5] = a.i;
+  }
+  __syncthreads();
+  ArgMax r = {redv[0], redi[0]};
+  for (int i = 1; i < LP_THREADS / 32; ++i) r = am_better(r, ArgMax{redv[i], redi[i]});
+  return r;
+}
+
+__global__ void __launch_bounds__(LP_THREADS, 1)
+process_logits_kernel(const float* __restrict__ logits, int64_t ld, const LogitRow* __restrict__ rows,
+                      LogitCfg cfg, PickOut* __restrict__ out) {
+  extern __shared__ __align__(16) float lg[];  // [n_vocab] masked logits, then probs
+  __shared__ float red[LP_THREADS / 32];
+  __shared__ int redi[LP_THREADS / 32];
+  __shared__ double redd[LP_THREADS / 32];
+  __shared__ double seg_prefix[LP_THREADS];
+  const LogitRow row = rows[blockIdx.x];
+  const float* src = logits + (int64_t)row.logits_row * ld;
+  const int n = cfg.n_vocab, beg = cfg.token_beg, tid = threadIdx.x;
+  const float NEG = -INFINITY;
+
+  // pass 0: raw softmax statistics (no_speech_prob), masked copy into smem
+  float rmax = NEG;
+  for (int i = tid; i < n; i += LP_THREADS) {
+    const float raw = src[i];
+    rmax = fmaxf(rmax, raw);
+    float v = row.temperature > 0.f ? raw / row.temperature : raw;
+    bool sup = cfg.d_suppress[i] != 0;
+    if (row.is_initial) {
+      if (cfg.suppress_blank && (i == cfg.token_eot || i == cfg.token_space)) sup = true;
+      if (i >= cfg.max_initial_ts_id) sup = true;
+    }
+    if (row.last_ts) {
+      if (row.penult_ts) {
+        if (i >= beg) sup = true;
+      } else {
+        if (i < cfg.token_eot) sup = true;
+      }
+    }
+    if (i >= beg && i < beg + row.ts_min) sup = true;
+    lg[i] = sup ? NEG : v;
+  }
+  rmax = block_max(rmax, red);
+  float rsum = 0.f;
+  for (int i = tid; i < n; i += LP_THREADS) rsum += expf(src[i] - rmax);
+  rsum = block_sum(rsum, red);
+  const float nosp = expf(src[cfg.token_nosp] - (logf(rsum) + rmax));
+
+  // log-softmax over the masked logits
+  float mx = NEG;
+  for (int i = tid; i < n; i += LP_THREADS) mx = fmaxf(mx, lg[i]);
+  mx = block_max(mx, red);
+  float se = 0.f;
+  for (int i = tid; i < n; i += LP_THREADS)
+    if (lg[i] > NEG) se += expf(lg[i] - mx);
+  se = block_sum(se, red);
+  const float lse = logf(se) + mx;
+
+  // timestamp mass vs best text token
+  float ts_mx = NEG, tx_mx = NEG;
+  for (int i = tid; i < n; i += LP_THREADS) {
+    const float lp = lg[i] > NEG ? lg[i] - lse : NEG;
+    if (i >= beg) ts_mx = fmaxf(ts_mx, lp);
+    else tx_mx = fmaxf(tx_mx, lp);
+  }
+  ts_mx = block_max(ts_mx, red);
+  tx_mx = block_max(tx_mx, red);
+  float ts_se = 0.f;
+  for (int i = beg + tid; i < n; i += LP_THREADS)
+    if (lg[i] > NEG) ts_se += expf((lg[i] - lse) - ts_mx);
+  ts_se = block_sum(ts_se, red);
+  const float ts_lp = ts_se > 0.f ? logf(ts_se) + ts_mx : NEG;
+  const bool force_ts = ts_lp > tx_mx;
+
+  // probs (in place), argmax, timestamp statistics
+  ArgMax best = {0.f, 0x7fffffff}, best_ts = {0.f, 0x7fffffff};
+  double sum_ts = 0.0, sum_all = 0.0;
+  for (int i = tid; i < n; i += LP_THREADS) {
+    float v = lg[i];
+    if (force_ts && i < beg) v = NEG;
+    const float p = v > NEG ? expf(v - lse) : 0.f;
+    lg[i] = p;
+    sum_all += (double)p;
+    if (p > best.v) best = ArgMax{p, i};
+    if (i >= beg) {
+      sum_ts += (double)p;
+      if (p > best_ts.v) best_ts = ArgMax{p, i};
+    }
+  }
+  best = block_argmax(best, red, redi);
+  best_ts = block_argmax(best_ts, red, redi);
+  sum_ts = block_sum_d(sum_ts, redd);
+  const int tid_ts = best_ts.i == 0x7fffffff ? 0 : best_ts.i;  // upstream starts from tid = 0
+  const float pt = (float)((double)best_ts.v / (sum_ts + 1e-10));
+  const float ptsum = (float)sum_ts;
+
+  PickOut* o = out + (int64_t)blockIdx.x * 8;
+  if (row.n_draws <= 0) {
+    if (tid == 0) {
+      PickOut r;
+      r.id = best.i == 0x7fffffff ? 0 : best.i;
+      r.p = best.i == 0x7fffffff ? 0.f : best.v;
+      r.plog = best.i == 0x7fffffff ? 0.f : logf(0.f);  // placeholder, fixed below
+      // plog = logprobs[id] = masked logit - lse; recompute from the unnormalised value
+      const float raw = src[r.id];
+      const float v = row.temperature > 0.f ? raw / row.temperature : raw;
+      r.plog = best.i == 0x7fffffff ? 0.f : v - lse;
+      r.tid = tid_ts;
+      r.pt = pt;
+      r.ptsum = ptsum;
+      if (r.id >= beg) {
+        r.tid = r.id;
+        r.pt = r.p;
+      }
+      r.no_speech_prob = nosp;
+      r.pad = 0;
+      o[0] = r;
+    }
+    return;
+  }
+  // ---- inverse-CDF draws (std::discrete_distribution: p_i / sum, partial sums, lower_bound(u))
+  sum_all = block_sum_d(sum_all, redd);
+  const int per = (n + LP_THREADS - 1) / LP_THREADS;
+  const int i0 = tid * per, i1 = min(n, i0 + per);
+  double loc = 0.0;
+  for (int i = i0; i < i1; ++i) loc += (double)lg[i] / sum_all;
+  seg_prefix[tid] = loc;
+  __syncthreads();
+  if (tid == 0) {
+    double run = 0.0;
+    for (int i = 0; i < LP_THREADS; ++i) {
+      const double t = seg_prefix[i];
+      seg_prefix[i] = run;  // exclusive
+      run += t;
+    }
+  }
+  __syncthreads();
+  __shared__ int draw_id[8];
+  if (tid < 8) draw_id[tid] = n - 1;  // cp.back() is forced to 1.0 upstream
+  __syncthreads();
+  for (int k = 0; k < row.n_draws && k < 8; ++k) {
+    const double u = row.u[k];
+    const double lo = seg_prefix[tid];
+    const double hi = (tid + 1 < LP_THREADS) ? seg_prefix[tid + 1] : 2.0;
+    if (i0 < i1 && lo < u && u <= hi) {  // first index whose inclusive prefix >= u lies in my segment
+      double run = lo;
+      int pick = i1 - 1;
+      for (int i = i0; i < i1; ++i) {
+        run += (double)lg[i] / sum_all;
+        if (run >= u) {
+          pick = i;
+          break;
+        }
+      }
+      atomicMin(&draw_id[k], pick);
+    }
+    if (tid == 0 && u <= 0.0) atomicMin(&draw_id[k], 0);
+  }
+  __syncthreads();
+  if (tid < row.n_draws && tid < 8) {
+    PickOut r;
+    r.id = draw_id[tid];
+    r.p = lg[r.id];
+    const float raw = src[r.id];
+    const float v = row.temperature > 0.f ? raw / row.temperature : raw;
+    r.plog = r.p > 0.f ? v - lse : -INFINITY;
+    r.tid = tid_ts;
+    r.pt = pt;
+    r.ptsum = ptsum;
+    if (r.id >= beg) {
+      r.tid = r.id;
+      r.pt = r.p;
+    }
+    r.no_speech_prob = nosp;
+    r.pad = 0;
+    o[tid] = r;
+  }
+}
+
+}  // namespace
+
+int kv_append(const bf16* qkv, const DecRow* d_rows, int R, int d, bf16* pool, const int* d_page_table,
+              int layer, int n_layer, cudaStream_t stream) {
+  if (R <= 0) return 0;
+  kv_append_kernel<<<R, 128, 0, stream>>>(qkv, d_rows, d, pool, d_page_table, layer, n_layer);
+  SW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int kv_copy_pages(bf16* pool, const int* d_pairs, int n, int64_t page_elems, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  kv_copy_pages_kernel<<<dim3(32, n), 256, 0, stream>>>(pool, d_pairs, page_elems);
+  SW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int self_attention(const bf16* qkv, const DecRow* d_rows, int R, int d, int n_head, const bf16* pool,
+                   const int* d_page_table, int layer, int n_layer, bf16* out, cudaStream_t stream) {
+  if (R <= 0) return 0;
+  SW_CHECK(d == n_head * 64, "self_attention: head dim must be 64");
+  self_attention_kernel<<<dim3(R, n_head), 128, 0, stream>>>(qkv, d_rows, d, pool, d_page_table, layer,
+                                                             n_layer, out);
+  SW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+size_t cross_attention_ws_floats(int R, int d, int n_head) {
+  // n_chunks <= ceil(1500/16/4) = 24 by construction (>= 4 stages per chunk)
+  return (size_t)R * 24 * (d + 2 * n_head);
+}
+
+int cross_attention(const bf16* q, const bf16* kv, const int* d_grp_win, const int* d_grp_start,
+                    const int* d_grp_count, int n_groups, int max_count, int R, int T, int d,
+                    int n_head, float* ws, bf16* out, cudaStream_t stream) {
+  if (n_groups <= 0 || R <= 0) return 0;
+  SW_CHECK(d == n_head * 64 && d % 8 == 0, "cross_attention: head dim must be 64");
+  SW_CHECK(max_count >= 1 && max_count <= XA_CONSUMERS, "cross_attention: group of %d rows", max_count);
+  int spc, n_chunks, n_stages;
+  xa_plan(n_groups, T, d, &spc, &n_chunks, &n_stages);
+  SW_CHECK(n_chunks <= 24, "cross_attention: %d chunks", n_chunks);
+  const int niter = (d / 8 + 31) / 32;
+  const int stage_bytes = XA_KEYS * 2 * d * 2;
+  size_t smem = (size_t)n_stages * stage_bytes + 2 * n_stages * sizeof(uint64_t);
+  const size_t merge = (size_t)XA_CONSUMERS * niter * 32 * 10 * sizeof(float);
+  if (smem < merge) smem = merge;
+  dim3 grid(n_chunks, n_groups);
+#define XA_LAUNCH(NI)                                                                              \
+  do {                                                                                             \
+    SW_CUDA_CHECK(cudaFuncSetAttribute(cross_attention_kernel<NI>,                                 \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    cross_attention_kernel<NI><<<grid, XA_THREADS, smem, stream>>>(                                \
+        q, kv, d_grp_win, d_grp_start, d_grp_count, T, d, n_head, spc, n_stages, n_chunks, ws);    \
+  } while (0)
+  switch (niter) {
+    case 1: XA_LAUNCH(1); break;
+    case 2: XA_LAUNCH(2); break;
+    case 3: XA_LAUNCH(3); break;
+    case 4: XA_LAUNCH(4); break;
+    case 5: XA_LAUNCH(5); break;
+    default: set_last_error("cross_attention: unsupported width %d", d); return -1;
+  }
+#undef XA_LAUNCH
+  SW_CUDA_CHECK(cudaGetLastError());
+  cross_combine_kernel<<<R, 160, 0, stream>>>(ws, n_chunks, d, n_head, out);
+  SW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int process_logits_pick(const float* logits, int64_t ld, const LogitRow* d_rows, int R,
+                        const LogitCfg& cfg, PickOut* d_out, cudaStream_t stream) {
+  if (R <= 0) return 0;
+  const size_t smem = (size_t)cfg.n_vocab * sizeof(float);
+  SW_CHECK(smem <= 210 * 1024, "process_logits: vocabulary of %d does not fit shared memory", cfg.n_vocab);
+  SW_CUDA_CHECK(cudaFuncSetAttribute(process_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+  process_logits_kernel<<<R, LP_THREADS, smem, stream>>>(logits, ld, d_rows, cfg, d_out);
+  SW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sw

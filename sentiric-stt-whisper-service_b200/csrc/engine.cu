@@ -1,0 +1,282 @@
+// Device pipelines of the engine (see engine.h): buffer setup, conv stem + encoder + cross-KV,
+// and one batched decoder step. Host control flow only; every arithmetic op is one of the
+// hand-written kernels in this directory (no cuBLAS/cuDNN/torch).
+#include "engine.h"
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace sw {
+
+Engine::~Engine() {
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (stream) cudaStreamDestroy(stream);
+  delete model;
+}
+
+static int engine_init(Engine* e, const char* path, const sw_ctx_params* p) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    set_last_error("no CUDA device: this library has no CPU fallback");
+    return -1;
+  }
+  e->device = p ? p->device : 0;
+  SW_CHECK(e->device >= 0 && e->device < n_dev, "device %d out of range (%d present)", e->device, n_dev);
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, e->device);
+  SW_CHECK(major == 10, "device %d has compute capability %d.x; this build is sm_100a only", e->device, major);
+  SW_CUDA_CHECK(cudaSetDevice(e->device));
+  e->max_batch = (p && p->max_batch > 0) ? p->max_batch : 64;
+  e->max_beams = (p && p->max_beams > 0) ? p->max_beams : 5;
+  SW_CHECK(e->max_beams <= 8, "max_beams %d > 8", e->max_beams);
+  e->max_rows = e->max_batch * e->max_beams;
+  e->model = load_model(path);
+  if (!e->model) return -1;
+  SW_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  SW_CUDA_CHECK(cudaEventCreate(&e->ev0));
+  SW_CUDA_CHECK(cudaEventCreate(&e->ev1));
+
+  const HParams& hp = e->model->hp;
+  const size_t d = hp.n_audio_state, nm = hp.n_mels, B = e->max_batch, R = e->max_rows;
+  const size_t M = B * 1500;
+  if (e->conv_in.alloc(B * 3002 * nm)) return -1;
+  if (e->h1.alloc(B * 3002 * d)) return -1;
+  SW_CUDA_CHECK(cudaMemset(e->h1.p, 0, B * 3002 * d * sizeof(bf16)));
+  if (e->x.alloc(M * d)) return -1;
+  if (e->hb.alloc(M * d)) return -1;
+  if (e->qkv.alloc(M * 3 * d)) return -1;
+  if (e->ff.alloc(M * 4 * d)) return -1;
+  if (e->cross_kv.alloc((size_t)hp.n_text_layer * M * 2 * d)) return -1;
+  // decoder
+  e->logits_ld = (hp.n_vocab + 3) / 4 * 4;
+  if (e->dx.alloc(R * d) || e->dh.alloc(R * d) || e->dqkv.alloc(R * 3 * d) || e->datt.alloc(R * d) ||
+      e->dq.alloc(R * d) || e->dff.alloc(R * 4 * d) || e->logits.alloc(R * e->logits_ld) ||
+      e->xa_ws.alloc(cross_attention_ws_floats((int)R, (int)d, hp.n_text_head)))
+    return -1;
+  e->n_pages = (int)(R * KV_MAX_PAGES + R);
+  const size_t page_elems = (size_t)hp.n_text_layer * 2 * KV_PAGE * d;
+  if (e->kv_pool.alloc((size_t)e->n_pages * page_elems)) return -1;
+  if (e->d_page_table.alloc(R * KV_MAX_PAGES) || e->d_tok.alloc(R) || e->d_pos.alloc(R) ||
+      e->d_grp_win.alloc(R) || e->d_grp_start.alloc(R) || e->d_grp_count.alloc(R) || e->d_rows.alloc(R) ||
+      e->d_lrows.alloc(R) || e->d_picks.alloc(R * 8) || e->d_suppress.alloc(hp.n_vocab) ||
+      e->d_copy_pairs.alloc(2 * R))
+    return -1;
+  if (e->h_page_table.alloc(R * KV_MAX_PAGES) || e->h_tok.alloc(R) || e->h_pos.alloc(R) ||
+      e->h_grp.alloc(3 * R) || e->h_rows.alloc(R) || e->h_lrows.alloc(R) || e->h_picks.alloc(R * 8))
+    return -1;
+  SW_CUDA_CHECK(cudaDeviceSynchronize());
+  log_msg(2, "model loaded: d=%d layers=%d/%d n_mels=%d n_vocab=%d; max_batch=%d max_beams=%d",
+          hp.n_audio_state, hp.n_audio_layer, hp.n_text_layer, hp.n_mels, hp.n_vocab, e->max_batch,
+          e->max_beams);
+  return 0;
+}
+
+Engine* engine_create(const char* model_path, const sw_ctx_params* params) {
+  Engine* e = new Engine();
+  if (engine_init(e, model_path, params)) {
+    delete e;
+    return nullptr;
+  }
+  return e;
+}
+
+#define GEMM(args)                                   \
+  do {                                               \
+    if (gemm_bf16_tn(args, e->stream)) return -1;    \
+    e->times.n_launches++;                           \
+  } while (0)
+
+int engine_encode(Engine* e, int n_win, float* enc_out_f32) {
+  const Model& m = *e->model;
+  const HParams& hp = m.hp;
+  const int d = hp.n_audio_state, nm = hp.n_mels;
+  const int64_t M = (int64_t)n_win * 1500;
+  SW_CHECK(n_win > 0 && n_win <= e->max_batch, "encode: %d windows exceed max_batch %d", n_win, e->max_batch);
+  cudaStream_t st = e->stream;
+  SW_CUDA_CHECK(cudaEventRecord(e->ev0, st));
+  {  // conv1 (k=3, s=1, p=1) as an implicit GEMM over overlapping rows of the padded input, + GELU
+    GemmArgs a;
+    a.A = e->conv_in.p; a.lda = nm; a.a_batch_stride = (int64_t)3002 * nm;
+    a.B = m.conv1_w; a.ldb = 3 * nm;
+    a.C = e->h1.p + d; a.ldc = d; a.c_batch_stride = (int64_t)3002 * d;
+    a.bias = m.conv1_b;
+    a.M = 3000; a.N = d; a.K = 3 * nm; a.batch = n_win;
+    a.flags = GEMM_GELU;
+    GEMM(a);
+  }
+  {  // conv2 (k=3, s=2, p=1) + GELU + positional embedding -> residual stream x (f32)
+    GemmArgs a;
+    a.A = e->h1.p; a.lda = 2 * d; a.a_batch_stride = (int64_t)3002 * d;
+    a.B = m.conv2_w; a.ldb = 3 * d;
+    a.C = e->x.p; a.ldc = d; a.c_batch_stride = (int64_t)1500 * d;
+    a.bias = m.conv2_b;
+    a.residual = m.enc_pos; a.ldr = d; a.r_batch_stride = 0; a.res_mod = 1500;
+    a.M = 1500; a.N = d; a.K = 3 * d; a.batch = n_win;
+    a.flags = GEMM_GELU | GEMM_OUT_F32;
+    GEMM(a);
+  }
+  for (int l = 0; l < hp.n_audio_layer; ++l) {
+    const EncLayerW& w = m.enc[l];
+    if (layer_norm(e->x.p, (int)M, d, w.ln1.g, w.ln1.b, e->hb.p, nullptr, nullptr, 0, 0, nullptr, st)) return -1;
+    {
+      GemmArgs a;
+      a.A = e->hb.p; a.lda = d; a.B = w.wqkv; a.ldb = d; a.C = e->qkv.p; a.ldc = 3 * d;
+      a.bias = w.bqkv; a.M = (int)M; a.N = 3 * d; a.K = d;
+      GEMM(a);
+    }
+    if (encoder_attention(e->qkv.p, e->hb.p, n_win, 1500, d, hp.n_audio_head, st)) return -1;
+    {
+      GemmArgs a;
+      a.A = e->hb.p; a.lda = d; a.B = w.wo; a.ldb = d; a.C = e->x.p; a.ldc = d;
+      a.bias = w.bo; a.residual = e->x.p; a.ldr = d; a.M = (int)M; a.N = d; a.K = d;
+      a.flags = GEMM_OUT_F32;
+      GEMM(a);
+    }
+    if (layer_norm(e->x.p, (int)M, d, w.ln2.g, w.ln2.b, e->hb.p, nullptr, nullptr, 0, 0, nullptr, st)) return -1;
+    {
+      GemmArgs a;
+      a.A = e->hb.p; a.lda = d; a.B = w.w1; a.ldb = d; a.C = e->ff.p; a.ldc = 4 * d;
+      a.bias = w.b1; a.M = (int)M; a.N = 4 * d; a.K = d; a.flags = GEMM_GELU;
+      GEMM(a);
+    }
+    {
+      GemmArgs a;
+      a.A = e->ff.p; a.lda = 4 * d; a.B = w.w2; a.ldb = 4 * d; a.C = e->x.p; a.ldc = d;
+      a.bias = w.b2; a.residual = e->x.p; a.ldr = d; a.M = (int)M; a.N = d; a.K = 4 * d;
+      a.flags = GEMM_OUT_F32;
+      GEMM(a);
+    }
+    e->times.n_launches += 3;
+  }
+  if (layer_norm(e->x.p, (int)M, d, m.ln_post.g, m.ln_post.b, e->hb.p, enc_out_f32, nullptr, 0, 0, nullptr, st))
+    return -1;
+  e->times.n_launches++;
+  const int64_t layer_stride = (int64_t)e->max_batch * 1500 * 2 * d;
+  for (int l = 0; l < hp.n_text_layer; ++l) {
+    const DecLayerW& w = m.dec[l];
+    GemmArgs a;
+    a.A = e->hb.p; a.lda = d; a.B = w.wxkv; a.ldb = d; a.C = e->cross_kv.p + l * layer_stride; a.ldc = 2 * d;
+    a.bias = w.bxkv; a.M = (int)M; a.N = 2 * d; a.K = d;
+    GEMM(a);
+  }
+  SW_CUDA_CHECK(cudaEventRecord(e->ev1, st));
+  SW_CUDA_CHECK(cudaEventSynchronize(e->ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->times.ms_encode += ms;
+  e->times.n_windows += n_win;
+  return 0;
+}
+
+int engine_copy_pages(Engine* e, const std::vector<int>& pairs) {
+  if (pairs.empty()) return 0;
+  const HParams& hp = e->model->hp;
+  const int n = (int)pairs.size() / 2;
+  SW_CHECK(pairs.size() <= e->d_copy_pairs.n, "too many page copies (%d)", n);
+  // pageable source: the driver stages it before returning, so the vector may die afterwards
+  SW_CUDA_CHECK(cudaMemcpyAsync(e->d_copy_pairs.p, pairs.data(), pairs.size() * sizeof(int),
+                                cudaMemcpyHostToDevice, e->stream));
+  const int64_t page_elems = (int64_t)hp.n_text_layer * 2 * KV_PAGE * hp.n_text_state;
+  if (kv_copy_pages(e->kv_pool.p, e->d_copy_pairs.p, n, page_elems, e->stream)) return -1;
+  e->times.n_launches++;
+  return 0;
+}
+
+int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_logits, int n_lrows,
+                       const LogitCfg& cfg, bool upload_page_table) {
+  const Model& m = *e->model;
+  const HParams& hp = m.hp;
+  const int d = hp.n_text_state, L = hp.n_text_layer;
+  SW_CHECK(R > 0 && R <= e->max_rows, "decode step with %d rows (max %d)", R, e->max_rows);
+  cudaStream_t st = e->stream;
+  SW_CUDA_CHECK(cudaEventRecord(e->ev0, st));
+  SW_CUDA_CHECK(cudaMemcpyAsync(e->d_rows.p, e->h_rows.p, R * sizeof(DecRow), cudaMemcpyHostToDevice, st));
+  SW_CUDA_CHECK(cudaMemcpyAsync(e->d_tok.p, e->h_tok.p, R * sizeof(int), cudaMemcpyHostToDevice, st));
+  SW_CUDA_CHECK(cudaMemcpyAsync(e->d_pos.p, e->h_pos.p, R * sizeof(int), cudaMemcpyHostToDevice, st));
+  SW_CUDA_CHECK(cudaMemcpyAsync(e->d_grp_win.p, e->h_grp.p, n_groups * sizeof(int), cudaMemcpyHostToDevice, st));
+  SW_CUDA_CHECK(cudaMemcpyAsync(e->d_grp_start.p, e->h_grp.p + e->max_rows, n_groups * sizeof(int), cudaMemcpyHostToDevice, st));
+  SW_CUDA_CHECK(cudaMemcpyAsync(e->d_grp_count.p, e->h_grp.p + 2 * e->max_rows, n_groups * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (upload_page_table)
+    SW_CUDA_CHECK(cudaMemcpyAsync(e->d_page_table.p, e->h_page_table.p,
+                                  (size_t)e->max_rows * KV_MAX_PAGES * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (embed_tokens(m.tok_emb, m.dec_pos, e->d_tok.p, e->d_pos.p, R, d, e->dx.p, st)) return -1;
+  const int64_t layer_stride = (int64_t)e->max_batch * 1500 * 2 * d;
+  for (int l = 0; l < L; ++l) {
+    const DecLayerW& w = m.dec[l];
+    if (layer_norm(e->dx.p, R, d, w.ln1.g, w.ln1.b, e->dh.p, nullptr, nullptr, 0, 0, nullptr, st)) return -1;
+    {
+      GemmArgs a;
+      a.A = e->dh.p; a.lda = d; a.B = w.wqkv; a.ldb = d; a.C = e->dqkv.p; a.ldc = 3 * d;
+      a.bias = w.bqkv; a.M = R; a.N = 3 * d; a.K = d;
+      GEMM(a);
+    }
+    if (kv_append(e->dqkv.p, e->d_rows.p, R, d, e->kv_pool.p, e->d_page_table.p, l, L, st)) return -1;
+    if (self_attention(e->dqkv.p, e->d_rows.p, R, d, hp.n_text_head, e->kv_pool.p, e->d_page_table.p, l, L,
+                       e->datt.p, st))
+      return -1;
+    {
+      GemmArgs a;
+      a.A = e->datt.p; a.lda = d; a.B = w.wo; a.ldb = d; a.C = e->dx.p; a.ldc = d;
+      a.bias = w.bo; a.residual = e->dx.p; a.ldr = d; a.M = R; a.N = d; a.K = d; a.flags = GEMM_OUT_F32;
+      GEMM(a);
+    }
+    if (layer_norm(e->dx.p, R, d, w.lnx.g, w.lnx.b, e->dh.p, nullptr, nullptr, 0, 0, nullptr, st)) return -1;
+    {
+      GemmArgs a;
+      a.A = e->dh.p; a.lda = d; a.B = w.wxq; a.ldb = d; a.C = e->dq.p; a.ldc = d;
+      a.bias = w.bxq; a.M = R; a.N = d; a.K = d;
+      GEMM(a);
+    }
+    if (cross_attention(e->dq.p, e->cross_kv.p + l * layer_stride, e->d_grp_win.p, e->d_grp_start.p,
+                        e->d_grp_count.p, n_groups, max_count, R, 1500, d, hp.n_text_head, e->xa_ws.p,
+                        e->datt.p, st))
+      return -1;
+    {
+      GemmArgs a;
+      a.A = e->datt.p; a.lda = d; a.B = w.wxo; a.ldb = d; a.C = e->dx.p; a.ldc = d;
+      a.bias = w.bxo; a.residual = e->dx.p; a.ldr = d; a.M = R; a.N = d; a.K = d; a.flags = GEMM_OUT_F32;
+      GEMM(a);
+    }
+    if (layer_norm(e->dx.p, R, d, w.ln2.g, w.ln2.b, e->dh.p, nullptr, nullptr, 0, 0, nullptr, st)) return -1;
+    {
+      GemmArgs a;
+      a.A = e->dh.p; a.lda = d; a.B = w.w1; a.ldb = d; a.C = e->dff.p; a.ldc = 4 * d;
+      a.bias = w.b1; a.M = R; a.N = 4 * d; a.K = d; a.flags = GEMM_GELU;
+      GEMM(a);
+    }
+    {
+      GemmArgs a;
+      a.A = e->dff.p; a.lda = 4 * d; a.B = w.w2; a.ldb = 4 * d; a.C = e->dx.p; a.ldc = d;
+      a.bias = w.b2; a.residual = e->dx.p; a.ldr = d; a.M = R; a.N = d; a.K = 4 * d; a.flags = GEMM_OUT_F32;
+      GEMM(a);
+    }
+    e->times.n_launches += 7;
+  }
+  e->times.n_launches += 1;
+  if (want_logits || n_lrows > 0) {
+    if (layer_norm(e->dx.p, R, d, m.dec_ln.g, m.dec_ln.b, e->dh.p, nullptr, nullptr, 0, 0, nullptr, st)) return -1;
+    GemmArgs a;
+    a.A = e->dh.p; a.lda = d; a.B = m.tok_emb; a.ldb = d; a.C = e->logits.p; a.ldc = e->logits_ld;
+    a.M = R; a.N = hp.n_vocab; a.K = d; a.flags = GEMM_OUT_F32;
+    GEMM(a);
+    e->times.n_launches += 1;
+  }
+  if (n_lrows > 0) {
+    SW_CUDA_CHECK(cudaMemcpyAsync(e->d_lrows.p, e->h_lrows.p, n_lrows * sizeof(LogitRow), cudaMemcpyHostToDevice, st));
+    if (process_logits_pick(e->logits.p, e->logits_ld, e->d_lrows.p, n_lrows, cfg, e->d_picks.p, st)) return -1;
+    SW_CUDA_CHECK(cudaMemcpyAsync(e->h_picks.p, e->d_picks.p, (size_t)n_lrows * 8 * sizeof(PickOut),
+                                  cudaMemcpyDeviceToHost, st));
+    e->times.n_launches += 1;
+  }
+  SW_CUDA_CHECK(cudaEventRecord(e->ev1, st));
+  SW_CUDA_CHECK(cudaEventSynchronize(e->ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->times.ms_decode += ms;
+  e->times.n_steps++;
+  return 0;
+}
+
+}  // namespace sw

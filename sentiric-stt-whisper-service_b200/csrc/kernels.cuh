@@ -1,0 +1,119 @@
+// Host-side launchers of the hand-written sm_100a kernels of the Whisper hot path
+// (everything whisper_full_with_state does on the device; reference call site
+// /root/reference/src/stt_engine.cpp:245-246). All launchers enqueue on `stream`
+// and return 0 or -1 (sw_last_error()).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sw {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ front end (mel.cu)
+constexpr int MEL_N_FFT = 400;
+constexpr int MEL_HOP = 160;
+constexpr int MEL_N_BINS = 201;
+constexpr int MEL_WIN_FRAMES = 3000;
+
+struct MelUtt {            // one utterance, device-side descriptor
+  int64_t pcm_off;         // element offset of its PCM in the batch PCM buffer
+  int n_samples;           //
+  int n_active;            // frames that see audio: min(n_eff/160 + 1, n_len)
+  int n_len;               // frames incl. the 30 s zero pad
+  int64_t log_off;         // element offset of its [n_mel][n_active] log-mel in the log buffer
+};
+// log10 mel power of every active frame (before clamp/normalise) + per-utterance max.
+// pcm is int16 (is_f32 = 0, scaled by 1/32768 in-register) or f32.
+int mel_log_power(const void* pcm, int is_f32, const MelUtt* d_utts, int n_utts, int max_active,
+                  const float* d_filters, int n_mel, float* d_log, unsigned* d_max_enc,
+                  cudaStream_t stream);
+// clamp to max-8, (x+4)/4; window w reads utterance win_utt[w] at frame win_seek[w].
+//   out_bf16: [n_win][3002][n_mel] time-major, rows 0 and 3001 zero (conv1's implicit-GEMM input)
+//   out_f32 : [n_win][n_mel][3000] mel-major (may be null)
+int mel_finalize_windows(const float* d_log, const MelUtt* d_utts, const unsigned* d_max_enc,
+                         const int* d_win_utt, const int* d_win_seek, int n_win, int n_mel,
+                         bf16* out_bf16, float* out_f32, cudaStream_t stream);
+// whole-utterance normalised mel [n_mel][n_len] f32 (the sw_mel_* hooks)
+int mel_finalize_full(const float* d_log, const MelUtt* d_utts, const unsigned* d_max_enc, int utt,
+                      int n_mel, int n_len, int n_active, float* out, cudaStream_t stream);
+// host mel [n_win][n_mel][3000] f32 -> conv1 input layout (the sw_encode hook)
+int mel_f32_to_conv_input(const float* d_mel, int n_win, int n_mel, bf16* out, cudaStream_t stream);
+// get_signal_energy (token-level timestamps): out[i] = sum_{|j|<=hw} |x[i+j]| / (2hw+1)
+int signal_energy(const void* pcm, int is_f32, int64_t off, int n, int hw, float* out,
+                  cudaStream_t stream);
+
+// ------------------------------------------------------------------ elementwise (elementwise.cu)
+// y = LN(x) * g + b over rows of d (eps 1e-5, f32 statistics). out_bf16/out_f32 may be null.
+// If partial != null: x += bias + sum_{s<n_split} partial[s][row][:] first (split-K reduce + residual).
+int layer_norm(float* x, int rows, int d, const float* g, const float* b, bf16* out_bf16,
+               float* out_f32, const float* partial, int n_split, int64_t split_stride,
+               const float* add_bias, cudaStream_t stream);
+// zero the pad rows (0 and 3001) of a [n_win][3002][d] bf16 buffer
+int zero_conv_pad_rows(bf16* buf, int n_win, int d, cudaStream_t stream);
+// x[r][:] = tok_emb[tok[r]][:] + pos_emb[pos[r]][:]
+int embed_tokens(const bf16* tok_emb, const float* pos_emb, const int* d_tok, const int* d_pos,
+                 int rows, int d, float* x, cudaStream_t stream);
+int convert_f16_to_bf16(const uint16_t* src, bf16* dst, int64_t n, cudaStream_t stream);
+int convert_f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t stream);
+
+// ------------------------------------------------------------------ encoder attention (attn_enc.cu)
+// non-causal MHA over T keys per (window, head); qkv [n_win*T][3d] bf16 (Q | K | V), out [n_win*T][d].
+int encoder_attention(const bf16* qkv, bf16* out, int n_win, int T, int d, int n_head,
+                      cudaStream_t stream);
+
+// ------------------------------------------------------------------ decoder (decode.cu)
+constexpr int KV_PAGE = 32;       // tokens per self-KV page
+constexpr int KV_MAX_PAGES = 14;  // 448 / 32
+
+struct DecRow {    // one decoder row of a step
+  int slot;        // self-KV slot (page table row)
+  int pos;         // position of this token
+  int win;         // window index into the cross-KV batch
+  int pad;
+};
+// append this step's K,V (qkv [R][3d] bf16) to the paged self-KV cache of layer `layer`.
+// pool layout: [page][layer][2][KV_PAGE][d]
+int kv_append(const bf16* qkv, const DecRow* d_rows, int R, int d, bf16* pool, const int* d_page_table,
+              int layer, int n_layer, cudaStream_t stream);
+// pool[dst page] = pool[src page] for n pairs (src, dst); page_elems bf16 elements per page
+int kv_copy_pages(bf16* pool, const int* d_pairs, int n, int64_t page_elems, cudaStream_t stream);
+// causal self attention of each row over cache[slot][0..pos]; out [R][d] bf16
+int self_attention(const bf16* qkv, const DecRow* d_rows, int R, int d, int n_head, const bf16* pool,
+                   const int* d_page_table, int layer, int n_layer, bf16* out, cudaStream_t stream);
+// cross attention: q [R][d] bf16; kv = cross-KV of this layer [n_win][T][2d] bf16 (K | V per key).
+// rows must be grouped by window: window g covers rows [grp_start[g], grp_start[g]+grp_count[g]).
+// workspace: f32, >= n_groups*n_chunks*max_cnt*(d + 2*n_head) ... see cross_attention_ws_floats().
+size_t cross_attention_ws_floats(int R, int d, int n_head);
+int cross_attention(const bf16* q, const bf16* kv, const int* d_grp_win, const int* d_grp_start,
+                    const int* d_grp_count, int n_groups, int max_count, int R, int T, int d,
+                    int n_head, float* ws, bf16* out, cudaStream_t stream);
+
+// logit rules + log-softmax + pick (whisper_process_logits + whisper_sample_token)
+struct LogitRow {        // per-row rule state, built by the host sequencer
+  int is_initial;        // no token sampled yet in this window
+  int last_ts;           // last sampled token was a timestamp
+  int penult_ts;         // the one before was (or fewer than 2 tokens)
+  int ts_min;            // has_ts ? seek_delta/2 : 0  -> timestamps below beg+ts_min suppressed
+  float temperature;     // > 0: logits /= temperature
+  int n_draws;           // 0: argmax; k>0: k inverse-CDF draws with the uniforms below
+  int logits_row;        // row of the logits matrix
+  int pad;
+  double u[8];           // uniforms for the draws (host mt19937, libstdc++ generate_canonical)
+};
+struct PickOut {         // per draw (n_draws or 1 entries per row, stride 8)
+  int id, tid;
+  float p, plog, pt, ptsum;
+  float no_speech_prob;  // softmax(raw logits)[nosp] (only meaningful on prompt rows)
+  int pad;
+};
+struct LogitCfg {
+  int n_vocab, token_eot, token_beg, token_nosp, token_space;
+  int suppress_blank, max_initial_ts_id;  // beg + tid0 + 1 (first suppressed), or n_vocab
+  const uint8_t* d_suppress;              // [n_vocab] 1 = always suppressed under these params
+};
+int process_logits_pick(const float* logits, int64_t ld, const LogitRow* d_rows, int R,
+                        const LogitCfg& cfg, PickOut* d_out, cudaStream_t stream);
+
+}  // namespace sw

@@ -1,0 +1,29 @@
+// Result containers behind the C ABI and the batched whisper_full_with_state entry point.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+struct sw_ctx {
+  sw::Engine* e = nullptr;
+};
+struct sw_segment {
+  int64_t t0 = 0, t1 = 0;
+  std::string text;
+  std::vector<sw_token_data> tokens;
+  bool speaker_turn_next = false;
+};
+struct sw_result {
+  std::vector<sw_segment> segs;
+  int lang_id = -1;
+  int n_decode_steps = 0;
+  int n_windows = 0;
+};
+
+namespace sw {
+// pcm[i]: n_samples[i] host samples (int16 or f32). out[i] receives a new sw_result.
+// Returns 0, or non-zero on failure/abort (all out[i] are null then).
+int run_full_batch(Engine* e, const sw_full_params* params, const void* const* pcm, const int* n_samples,
+                   int n, bool is_f32, sw_result** out);
+}  // namespace sw

@@ -1,0 +1,306 @@
+#!/usr/bin/env python3
+"""Benchmark of the Whisper hot path on B200 (BASELINE.json: audio-sec/sec, large-v3).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (oracle; see below)
+
+Workload (BASELINE.json configs[4], the configuration the metric is quoted on, per GPU):
+Whisper large-v3 (128 mel), greedy, batch 64, 128 x 30 s windows per GPU per step (1024 windows
+over 8 GPUs), synthetic 16 kHz speech-like audio, seeded synthetic ggml weights whose decoder
+follows a scripted ~100-token timestamped transcript. One "step" = one pass of the whole hot
+path (PCM -> log-mel -> conv stem -> encoder -> cross-KV -> greedy decode -> segments) over the
+rank's 128 windows. Windows are independent: ranks share nothing (weak scaling, no collective on
+the data path); torch.distributed is used only for the barrier and the max-over-ranks time.
+
+`value` : audio-seconds per second with the PCM already resident in HBM (device pointers in).
+`e2e`   : the same through the reference-facing C-ABI call with pinned HOST buffers (H2D of the
+          PCM and the D2H read-back of picks / token-timestamp energy inside the timed region).
+The reference arm (`--impl reference`) times the CPU oracle (a restatement of whisper.cpp v1.8.2,
+"CPU restatement, not ggml": the reference's own whisper.cpp cannot be built here) on a
+bounded sample of the same workload: one window per step, all host threads.
+"""
+import argparse
+import ctypes as C
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = os.path.join(ROOT, "sentiric-stt-whisper-service_b200")
+
+SERVICE_PARAMS = dict(  # what SttEngine::transcribe sets (stt_engine.cpp:204-243) with config.h defaults
+    language="en", token_timestamps=1, suppress_nst=1, no_speech_thold=0.85, logprob_thold=-0.7,
+    entropy_thold=2.40, temperature=0.0)
+
+
+def load_binding():
+    spec = importlib.util.spec_from_file_location("sw_binding", os.path.join(PKG, "sw_binding.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"],
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def model_path(size, script_len):
+    return "/tmp/sw_bench_%s_s%d.bin" % (size, script_len)
+
+
+def ensure_model(size, script_len):
+    from tools import gen_model
+    path = model_path(size, script_len)
+    if not os.path.exists(path):
+        tmp = path + ".tmp%d" % os.getpid()
+        gen_model.generate(tmp, size, script_len=script_len)
+        os.replace(tmp, path)
+    return path
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle on the host cores, one 30 s window of the same workload per step."""
+    if rank != 0:
+        return
+    from oracle import ora
+    from tools import synth_audio
+    path = ensure_model(args.model, args.script_len)
+    cores = os.cpu_count() or 1
+    o = ora.Oracle(path, weight_round=False, act_round=ora.ACT_F16, threads=cores)
+    p = o.default_params(0, **SERVICE_PARAMS)
+    times = []
+    for s in range(args.warmup + args.steps):
+        pcm = synth_audio.to_f32(synth_audio.utterance(5, s))
+        t0 = time.perf_counter()
+        r = o.full(pcm, p)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    val = 30.0 * len(times) / total
+    line = dict(
+        impl="reference", metric="audio-sec/sec (RTFx)", value=val, unit="audio-sec/sec",
+        n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * total / len(times),
+        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16 weights, f32 accumulate",
+        data="synthetic",
+        config=dict(workload="whisper %s greedy, one 30 s window per step (bounded sample of the "
+                             "128-window step)" % args.model, script_tokens=args.script_len),
+        cpu_baseline=dict(value=val, unit="audio-sec/sec", cores=cores, kind="port",
+                          sample="1 x 30 s window per step, %d steps; CPU restatement of whisper.cpp "
+                                 "v1.8.2, not ggml" % args.steps),
+        e2e=dict(value=val, unit="audio-sec/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        n_decode_steps=r["n_decode_steps"])
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="large-v3")
+    ap.add_argument("--windows-per-gpu", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--script-len", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- model (rank 0 of the node generates the seeded file once)
+    if local_rank == 0:
+        ensure_model(args.model, args.script_len)
+    barrier()
+    path = model_path(args.model, args.script_len)
+
+    swb = load_binding()
+    from tools import synth_audio
+    eng = swb.Engine(path, device=local_rank, max_batch=args.batch, max_beams=5)
+    params = eng.default_params(0, **SERVICE_PARAMS)  # greedy, best_of 5, temperature_inc 0.2 (defaults)
+    eng.set_kernel_timing(True)
+
+    # ---- inputs: W windows of 30 s int16, pinned host copy + device copy
+    W = args.windows_per_gpu
+    n_s = 480000
+    L = swb.lib()
+    host = L.sw_host_alloc(W * n_s * 2)
+    if not host:
+        raise SystemExit("pinned allocation failed: " + swb.last_error())
+    host_np = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_int16)), shape=(W, n_s))
+    for i in range(W):
+        host_np[i] = synth_audio.utterance(5, rank * W + i)
+    dev = torch.from_numpy(host_np.copy()).cuda()
+    lens = (C.c_int * W)(*([n_s] * W))
+    ptr16 = C.POINTER(C.c_int16)
+    host_ptrs = (ptr16 * W)(*[C.cast(host + i * n_s * 2, ptr16) for i in range(W)])
+    dev_ptrs = (ptr16 * W)(*[C.cast(dev.data_ptr() + i * n_s * 2, ptr16) for i in range(W)])
+
+    def step(ptrs):
+        res = eng.full_batch_ptrs(ptrs, lens, W, params)
+        n_tok = 0
+        for r in res:
+            for s in range(L.sw_result_n_segments(r)):
+                n_tok += L.sw_result_n_tokens(r, s)
+            L.sw_result_free(r)
+        return n_tok
+
+    def timed(ptrs, k):
+        barrier()
+        t0 = time.perf_counter()
+        n_tok = 0
+        for _ in range(k):
+            n_tok += step(ptrs)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, n_tok
+
+    for _ in range(args.warmup):
+        step(dev_ptrs)
+    eng.stats(reset=True)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    dt, n_tok = timed(dev_ptrs, args.steps)
+    st = eng.stats(reset=True)
+    dt_e2e, _ = timed(host_ptrs, args.steps)
+    st_e2e = eng.stats(reset=True)
+    clk = clocks.stop()
+
+    audio_s = 30.0 * W * world * args.steps
+    value = audio_s / dt
+    e2e = audio_s / dt_e2e
+    pk = peaks()
+    info = eng.info
+    d, Le, Ld, nm = info.n_audio_state, info.n_audio_layer, info.n_text_layer, info.n_mels
+    flops_win = (2 * 3000 * nm * 3 * d + 2 * 1500 * d * 3 * d + Le * (24 * 1500 * d * d + 4 * 1500 * 1500 * d)
+                 + Ld * 4 * 1500 * d * d)
+    xa_ms = st["ms_xattn"] / max(1, st["n_xattn"])
+    xa_bytes = st["xattn_bytes"] / max(1, st["n_xattn"])
+    xa_gbs = xa_bytes / (xa_ms * 1e-3) / 1e9 if xa_ms > 0 else 0.0
+    enc_tf = flops_win * st["n_windows"] / (st["ms_encode"] * 1e-3) / 1e12 if st["ms_encode"] > 0 else 0.0
+    dec_gbs = st["decode_bytes"] / (st["ms_decode"] * 1e-3) / 1e9 if st["ms_decode"] > 0 else 0.0
+
+    line = dict(
+        metric="audio-sec/sec (RTFx)", value=value, unit="audio-sec/sec", n_gpus=world,
+        steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * dt / args.steps,
+        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16 (f32 accumulate)",
+        data="synthetic",
+        config=dict(workload="whisper %s greedy batch-%d, %d x 30 s windows per GPU per step "
+                             "(BASELINE configs[4] share of one GPU)" % (args.model, args.batch, W),
+                    windows_per_gpu=W, batch=args.batch, script_tokens=args.script_len,
+                    params="SttEngine defaults: greedy, token_timestamps, suppress_nst, temperature_inc 0.2",
+                    l2="per-step working set (cross-KV %.1f GB) exceeds the 126 MB L2" %
+                       (Ld * 2 * 1500 * d * 2 * args.batch / 1e9)),
+        e2e=dict(value=e2e, unit="audio-sec/sec",
+                 h2d_bytes_per_step=int(st_e2e["h2d_bytes"] / args.steps),
+                 d2h_bytes_per_step=int(st_e2e["d2h_bytes"] / args.steps)),
+        gpu_launches=int(st["n_launches"]),
+        clocks=clk,
+        roofline=dict(bound="hbm", kernel="cross_attention_kernel", achieved=xa_gbs, peak=pk["hbm"],
+                      unit="GB/s", frac=xa_gbs / pk["hbm"], traffic=None,
+                      avg_launch_ms=xa_ms, algorithmic_bytes_per_launch=xa_bytes, peak_source=pk["src"]),
+        stages=dict(
+            tokens_per_window=n_tok / max(1, W * args.steps),
+            decode_steps=int(st["n_steps"] / args.steps),
+            device_ms_per_step=dict(mel=st["ms_mel"] / args.steps, encode=st["ms_encode"] / args.steps,
+                                    decode=st["ms_decode"] / args.steps),
+            encoder_ms_per_window=st["ms_encode"] / max(1, st["n_windows"]),
+            encoder_tflops=enc_tf, encoder_frac_of_sustained_peak=enc_tf / pk["tf_sust"],
+            decode_gbs=dec_gbs, decode_frac_of_hbm=dec_gbs / pk["hbm"]))
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ora
+        cores = os.cpu_count() or 1
+        o = ora.Oracle(path, weight_round=False, act_round=ora.ACT_F16, threads=cores)
+        po = o.default_params(0, **SERVICE_PARAMS)
+        pcm = synth_audio.to_f32(host_np[0])
+        t0 = time.perf_counter()
+        r = o.full(pcm, po)
+        dtc = time.perf_counter() - t0
+        line["cpu_baseline"] = dict(
+            value=30.0 / dtc, unit="audio-sec/sec", cores=cores, kind="port",
+            sample="1 of the %d windows (30 s audio), %.1f s of CPU; CPU restatement of whisper.cpp "
+                   "v1.8.2, not ggml" % (W, dtc))
+        o.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    L.sw_host_free(host)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -157,7 +157,13 @@ typedef struct sw_stats {
   long n_windows, n_steps, n_launches; /* windows encoded, decoder steps, kernels launched */
   double decode_bytes;                 /* algorithmic bytes of the sampled decode steps */
   double decoder_weight_bytes;         /* bytes of decoder weights one step streams */
+  double h2d_bytes, d2h_bytes;         /* PCM uploaded / picks + token-timestamp energy read back */
+  double ms_xattn;                     /* device time inside cross-attention launches (kernel timing on) */
+  long n_xattn;                        /* number of those launches */
+  double xattn_bytes;                  /* their algorithmic bytes (cross-KV of the active windows, q, out) */
 } sw_stats;
+/* bracket every cross-attention launch with CUDA events on the engine's stream (bench roofline) */
+SW_API void sw_ctx_set_kernel_timing(sw_ctx* ctx, int on);
 SW_API int sw_ctx_get_stats(sw_ctx* ctx, sw_stats* out, int reset);
 
 /* ---- stage-level hooks (parity tests and roofline measurement) --------- *

@@ -146,6 +146,10 @@ int sw_result_n_decode_steps(const sw_result* r) { return r ? r->n_decode_steps 
 int sw_result_n_windows(const sw_result* r) { return r ? r->n_windows : 0; }
 void sw_result_free(sw_result* r) { delete r; }
 
+void sw_ctx_set_kernel_timing(sw_ctx* ctx, int on) {
+  if (ctx) ctx->e->kernel_timing = on != 0;
+}
+
 int sw_ctx_get_stats(sw_ctx* ctx, sw_stats* out, int reset) {
   if (!ctx || !out) {
     set_last_error("null argument");
@@ -155,6 +159,8 @@ int sw_ctx_get_stats(sw_ctx* ctx, sw_stats* out, int reset) {
   out->ms_mel = t.ms_mel; out->ms_encode = t.ms_encode; out->ms_decode = t.ms_decode;
   out->n_windows = t.n_windows; out->n_steps = t.n_steps; out->n_launches = t.n_launches;
   out->decode_bytes = t.decode_bytes;
+  out->h2d_bytes = t.h2d_bytes; out->d2h_bytes = t.d2h_bytes;
+  out->ms_xattn = t.ms_xattn; out->n_xattn = t.n_xattn; out->xattn_bytes = t.xattn_bytes;
   out->decoder_weight_bytes = (double)ctx->e->model->weight_bytes_decoder;
   if (reset) t = sw::StageTimes();
   return 0;

@@ -11,6 +11,8 @@ namespace sw {
 Engine::~Engine() {
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
+  for (auto ev : xa_ev)
+    if (ev) cudaEventDestroy(ev);
   if (stream) cudaStreamDestroy(stream);
   delete model;
 }
@@ -37,6 +39,8 @@ static int engine_init(Engine* e, const char* path, const sw_ctx_params* p) {
   SW_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   SW_CUDA_CHECK(cudaEventCreate(&e->ev0));
   SW_CUDA_CHECK(cudaEventCreate(&e->ev1));
+  e->xa_ev.assign(2 * (size_t)64, nullptr);
+  for (auto& ev : e->xa_ev) SW_CUDA_CHECK(cudaEventCreate(&ev));
 
   const HParams& hp = e->model->hp;
   const size_t d = hp.n_audio_state, nm = hp.n_mels, B = e->max_batch, R = e->max_rows;
@@ -229,10 +233,12 @@ int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_
       a.bias = w.bxq; a.M = R; a.N = d; a.K = d;
       GEMM(a);
     }
+    if (e->kernel_timing) SW_CUDA_CHECK(cudaEventRecord(e->xa_ev[2 * l], st));
     if (cross_attention(e->dq.p, e->cross_kv.p + l * layer_stride, e->d_grp_win.p, e->d_grp_start.p,
                         e->d_grp_count.p, n_groups, max_count, R, 1500, d, hp.n_text_head, e->xa_ws.p,
                         e->datt.p, st))
       return -1;
+    if (e->kernel_timing) SW_CUDA_CHECK(cudaEventRecord(e->xa_ev[2 * l + 1], st));
     {
       GemmArgs a;
       a.A = e->datt.p; a.lda = d; a.B = w.wxo; a.ldb = d; a.C = e->dx.p; a.ldc = d;
@@ -276,6 +282,17 @@ int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->times.ms_decode += ms;
   e->times.n_steps++;
+  if (n_lrows > 0) e->times.d2h_bytes += (double)n_lrows * 8 * sizeof(PickOut);
+  if (e->kernel_timing) {
+    for (int l = 0; l < L; ++l) {
+      float t = 0;
+      cudaEventElapsedTime(&t, e->xa_ev[2 * l], e->xa_ev[2 * l + 1]);
+      e->times.ms_xattn += t;
+    }
+    e->times.n_xattn += L;
+    // per launch: the cross-KV of every active window once + q in + attention out
+    e->times.xattn_bytes += (double)L * ((double)n_groups * 1500 * 2 * d * 2 + (double)R * d * 4);
+  }
   return 0;
 }
 

@@ -18,6 +18,10 @@ namespace sw {
 struct StageTimes {  // accumulated device time per stage (CUDA events), for the benchmark
   double ms_mel = 0, ms_encode = 0, ms_decode = 0;
   long n_windows = 0, n_steps = 0, n_launches = 0;
+  double h2d_bytes = 0, d2h_bytes = 0;  // PCM in, picks / energy out
+  double ms_xattn = 0;        // device time inside cross_attention launches (kernel timing on)
+  long n_xattn = 0;
+  double xattn_bytes = 0;     // algorithmic bytes of those launches (cross-KV of the active windows)
   double decode_bytes = 0;  // algorithmic bytes streamed by the decode steps (weights + cross-KV + self-KV)
 };
 
@@ -46,9 +50,12 @@ struct PinBuf {
     SW_CUDA_CHECK(cudaMallocHost(&p, count * sizeof(T)));
     return 0;
   }
-  ~PinBuf() {
+  void release() {
     if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
   }
+  ~PinBuf() { release(); }
 };
 
 struct Engine {
@@ -66,6 +73,9 @@ struct Engine {
   DevBuf<MelUtt> d_utts;
   DevBuf<unsigned> d_max_enc;
   DevBuf<int> d_win_utt, d_win_seek;
+  DevBuf<float> d_energy;       // token-timestamp signal energy, same offsets as the PCM
+  PinBuf<float> h_energy;
+  size_t energy_capacity = 0;
   int utt_capacity = 0;
   // ---- encoder activations (max_batch windows)
   DevBuf<bf16> conv_in, h1, hb, qkv, ff;
@@ -90,6 +100,8 @@ struct Engine {
 
   StageTimes times;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool kernel_timing = false;   // bracket each cross_attention launch with events (bench roofline)
+  std::vector<cudaEvent_t> xa_ev;
 
   ~Engine();
 };

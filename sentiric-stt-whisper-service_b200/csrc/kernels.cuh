@@ -40,9 +40,10 @@ int mel_finalize_full(const float* d_log, const MelUtt* d_utts, const unsigned* 
                       int n_mel, int n_len, int n_active, float* out, cudaStream_t stream);
 // host mel [n_win][n_mel][3000] f32 -> conv1 input layout (the sw_encode hook)
 int mel_f32_to_conv_input(const float* d_mel, int n_win, int n_mel, bf16* out, cudaStream_t stream);
-// get_signal_energy (token-level timestamps): out[i] = sum_{|j|<=hw} |x[i+j]| / (2hw+1)
-int signal_energy(const void* pcm, int is_f32, int64_t off, int n, int hw, float* out,
-                  cudaStream_t stream);
+// get_signal_energy (token-level timestamps) for every utterance of the batch:
+// out[pcm_off + i] = sum_{|j|<=hw} |x[i+j]| / (2hw+1), summed in upstream's order (bit-exact)
+int signal_energy(const void* pcm, int is_f32, const MelUtt* d_utts, int n_utts, int max_n, int hw,
+                  float* out, cudaStream_t stream);
 
 // ------------------------------------------------------------------ elementwise (elementwise.cu)
 // y = LN(x) * g + b over rows of d (eps 1e-5, f32 statistics). out_bf16/out_f32 may be null.

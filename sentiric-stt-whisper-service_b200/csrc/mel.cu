@@ -238,12 +238,16 @@ mel_f32_to_conv_input_kernel(const float* __restrict__ mel, int n_mel, bf16* __r
 
 template <bool F32>
 __global__ void __launch_bounds__(256)
-signal_energy_kernel(const void* __restrict__ pcm, int64_t off, int n, int hw, float* __restrict__ out) {
+signal_energy_kernel(const void* __restrict__ pcm, const MelUtt* __restrict__ utts, int hw,
+                     float* __restrict__ out) {
   extern __shared__ float sh[];  // 256 + 2*hw, |x|
+  const MelUtt u = utts[blockIdx.y];
+  const int n = u.n_samples;
+  if ((int)blockIdx.x * 256 >= n) return;
   const int base = blockIdx.x * 256 - hw;
   for (int i = threadIdx.x; i < 256 + 2 * hw; i += 256) {
     const int s = base + i;
-    sh[i] = (s >= 0 && s < n) ? fabsf(load_sample<F32>(pcm, off, s)) : 0.f;
+    sh[i] = (s >= 0 && s < n) ? fabsf(load_sample<F32>(pcm, u.pcm_off, s)) : 0.f;
   }
   __syncthreads();
   const int i = blockIdx.x * 256 + threadIdx.x;
@@ -251,7 +255,7 @@ signal_energy_kernel(const void* __restrict__ pcm, int64_t off, int n, int hw, f
   float sum = 0.f;
   for (int j = -hw; j <= hw; ++j)
     if (i + j >= 0 && i + j < n) sum = __fadd_rn(sum, sh[threadIdx.x + hw + j]);
-  out[i] = sum / (float)(2 * hw + 1);
+  out[u.pcm_off + i] = sum / (float)(2 * hw + 1);
 }
 
 }  // namespace
@@ -298,15 +302,15 @@ int mel_f32_to_conv_input(const float* d_mel, int n_win, int n_mel, bf16* out, c
   return 0;
 }
 
-int signal_energy(const void* pcm, int is_f32, int64_t off, int n, int hw, float* out,
-                  cudaStream_t stream) {
-  if (n <= 0) return 0;
-  const int grid = (n + 255) / 256;
+int signal_energy(const void* pcm, int is_f32, const MelUtt* d_utts, int n_utts, int max_n, int hw,
+                  float* out, cudaStream_t stream) {
+  if (n_utts <= 0 || max_n <= 0) return 0;
+  dim3 grid((max_n + 255) / 256, n_utts);
   const size_t sh = (256 + 2 * hw) * sizeof(float);
   if (is_f32)
-    signal_energy_kernel<true><<<grid, 256, sh, stream>>>(pcm, off, n, hw, out);
+    signal_energy_kernel<true><<<grid, 256, sh, stream>>>(pcm, d_utts, hw, out);
   else
-    signal_energy_kernel<false><<<grid, 256, sh, stream>>>(pcm, off, n, hw, out);
+    signal_energy_kernel<false><<<grid, 256, sh, stream>>>(pcm, d_utts, hw, out);
   SW_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

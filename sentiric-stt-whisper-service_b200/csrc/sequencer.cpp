@@ -38,7 +38,8 @@ struct Utt {
   int seek = 0, seek_end = 0;
   std::vector<int> prompt_past;
   std::mt19937 rng[8];
-  std::vector<float> energy;
+  const float* energy = nullptr;  // smoothed |x| (pinned host buffer of the engine)
+  int n_energy = 0;
   int64_t t_beg = 0, t_last = 0;
   int tid_last = 0;
   sw_result* res = nullptr;
@@ -159,7 +160,7 @@ inline int64_t sample_to_ts(int i) { return (100ll * i) / SR; }
 void token_timestamps(const Model& m, Utt& u, sw_segment& seg) {
   const float thold_pt = 0.01f, thold_ptsum = 0.01f;
   auto& tk = seg.tokens;
-  const int n_samples = (int)u.energy.size();
+  const int n_samples = u.n_energy;
   const int n = (int)tk.size();
   if (n_samples == 0 || n == 0) return;
   const int64_t t0 = seg.t0, t1 = seg.t1;
@@ -221,7 +222,7 @@ void token_timestamps(const Model& m, Utt& u, sw_segment& seg) {
     }
   }
   // expand / contract on the smoothed signal energy
-  const std::vector<float>& en = u.energy;
+  const float* en = u.energy;
   const int hw = SR / 8;
   for (int j = 0; j < n; ++j) {
     if (tk[j].id >= m.vocab.eot) continue;
@@ -381,7 +382,7 @@ struct Run {
     for (int i = 0; i < n; ++i)
       if (n_samples[i] > 0)
         SW_CUDA_CHECK(cudaMemcpyAsync(e->d_pcm.p + mu[i].pcm_off * es, pcm[i], (size_t)n_samples[i] * es,
-                                      cudaMemcpyHostToDevice, st));
+                                      cudaMemcpyDefault, st));  // host (pageable/pinned) or device source
     SW_CUDA_CHECK(cudaMemcpyAsync(e->d_utts.p, mu.data(), n * sizeof(MelUtt), cudaMemcpyHostToDevice, st));
     // running max starts at log10(1e-10) = -10: every utterance has zero-pad frames
     std::vector<unsigned> init(n);
@@ -396,21 +397,22 @@ struct Run {
                       e->d_max_enc.p, st))
       return -1;
     e->times.n_launches++;
-    if (p.token_timestamps) {
-      DevBuf<float> d_en;
+    if (p.token_timestamps && pcm_off > 0) {
       int max_n = 0;
       for (int i = 0; i < n; ++i) max_n = std::max(max_n, n_samples[i]);
-      if (max_n > 0) {
-        if (d_en.alloc(max_n)) return -1;
-        for (int i = 0; i < n; ++i) {
-          Utt& u = utts[i];
-          u.energy.resize(u.n_samples);
-          if (u.n_samples == 0) continue;
-          if (signal_energy(e->d_pcm.p, is_f32, mu[i].pcm_off, u.n_samples, 32, d_en.p, st)) return -1;
-          e->times.n_launches++;
-          SW_CUDA_CHECK(cudaMemcpyAsync(u.energy.data(), d_en.p, (size_t)u.n_samples * 4, cudaMemcpyDeviceToHost, st));
-          SW_CUDA_CHECK(cudaStreamSynchronize(st));
-        }
+      if ((size_t)pcm_off > e->energy_capacity) {
+        e->d_energy.release();
+        e->h_energy.release();
+        e->energy_capacity = (size_t)pcm_off * 5 / 4 + 1024;
+        if (e->d_energy.alloc(e->energy_capacity) || e->h_energy.alloc(e->energy_capacity)) return -1;
+      }
+      if (signal_energy(e->d_pcm.p, is_f32, e->d_utts.p, n, max_n, 32, e->d_energy.p, st)) return -1;
+      e->times.n_launches++;
+      SW_CUDA_CHECK(cudaMemcpyAsync(e->h_energy.p, e->d_energy.p, (size_t)pcm_off * 4, cudaMemcpyDeviceToHost, st));
+      e->times.d2h_bytes += (double)pcm_off * 4;
+      for (int i = 0; i < n; ++i) {
+        utts[i].energy = e->h_energy.p + mu[i].pcm_off;
+        utts[i].n_energy = n_samples[i];
       }
     }
     SW_CUDA_CHECK(cudaEventRecord(e->ev1, st));
@@ -418,6 +420,7 @@ struct Run {
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev0, e->ev1);
     e->times.ms_mel += ms;
+    for (int i = 0; i < n; ++i) e->times.h2d_bytes += (double)n_samples[i] * es;
     return 0;
   }
 

@@ -53,7 +53,9 @@ class TokenData(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ms_mel", C.c_double), ("ms_encode", C.c_double), ("ms_decode", C.c_double),
                 ("n_windows", C.c_long), ("n_steps", C.c_long), ("n_launches", C.c_long),
-                ("decode_bytes", C.c_double), ("decoder_weight_bytes", C.c_double)]
+                ("decode_bytes", C.c_double), ("decoder_weight_bytes", C.c_double),
+                ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double), ("ms_xattn", C.c_double),
+                ("n_xattn", C.c_long), ("xattn_bytes", C.c_double)]
 
 
 EXPORTS = [
@@ -64,7 +66,7 @@ EXPORTS = [
     "sw_result_segment_text", "sw_result_segment_t0", "sw_result_segment_t1",
     "sw_result_segment_speaker_turn_next", "sw_result_n_tokens", "sw_result_token_data",
     "sw_result_lang_id", "sw_result_n_decode_steps", "sw_result_n_windows", "sw_result_free",
-    "sw_ctx_get_stats", "sw_mel_pcm16", "sw_mel_f32", "sw_encode", "sw_decode_logits",
+    "sw_ctx_get_stats", "sw_ctx_set_kernel_timing", "sw_mel_pcm16", "sw_mel_f32", "sw_encode", "sw_decode_logits",
     "sw_dev_gemm_bf16"]
 
 _lib = None
@@ -116,6 +118,7 @@ def lib():
         getattr(L, "sw_result_" + n).argtypes = [vp]
     L.sw_result_free.argtypes = [vp]
     L.sw_ctx_get_stats.argtypes = [vp, C.POINTER(Stats), ci]
+    L.sw_ctx_set_kernel_timing.argtypes = [vp, ci]
     L.sw_mel_pcm16.argtypes = [vp, C.POINTER(C.c_int16), ci, fp, C.POINTER(ci)]
     L.sw_mel_f32.argtypes = [vp, fp, ci, fp, C.POINTER(ci)]
     L.sw_encode.argtypes = [vp, fp, ci, fp]
@@ -253,6 +256,9 @@ class Engine:
         if self.L.sw_decode_logits(self.h, t.ctypes.data_as(C.POINTER(C.c_int32)), n, k, _fp(out)):
             raise RuntimeError(last_error())
         return out
+
+    def set_kernel_timing(self, on):
+        self.L.sw_ctx_set_kernel_timing(self.h, int(on))
 
     def stats(self, reset=False):
         s = Stats()

@@ -1,0 +1,310 @@
+"""GPU parity tests (run with -m gpu on a B200): every stage and the whole path through the C ABI
+against the CPU oracle on the same seeded inputs. Tolerances are the ones BASELINE.json's
+north_star states: log-mel within 1e-3 relative; encoder within a stated bf16 tolerance (2e-2 of the
+output range against the f16 "whisper.cpp-mode" oracle, 1e-2 against the bf16-mode oracle); greedy
+token sequences identical."""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+from conftest import model_file, seg_ids
+from tools import synth_audio
+
+pytestmark = pytest.mark.gpu
+
+GREEDY = dict(language="en", temperature_inc=0.0, suppress_nst=1, token_timestamps=1)
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(1e-9, np.abs(b).max()))
+
+
+@pytest.fixture(scope="module")
+def eng_micro(swb, micro_model):
+    e = swb.Engine(micro_model[0], max_batch=8, max_beams=5)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng_tiny(swb, tiny_model):
+    e = swb.Engine(tiny_model[0], max_batch=8, max_beams=5)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def ora_micro(ora, micro_model):
+    return ora.Oracle(micro_model[0], weight_round=False, act_round=ora.ACT_F16)
+
+
+@pytest.fixture(scope="module")
+def ora_tiny(ora, tiny_model):
+    return ora.Oracle(tiny_model[0], weight_round=False, act_round=ora.ACT_F16)
+
+
+# ---------------------------------------------------------------- front end
+@pytest.mark.parametrize("seconds", [0.0, 0.05, 0.7, 1.0, 5.33, 12.0, 30.0, 41.5])
+def test_mel_parity_ragged_lengths(eng_micro, ora_micro, seconds):
+    pcm16 = synth_audio.utterance(2, int(seconds * 10), seconds=max(seconds, 0.01))[: int(seconds * 16000)]
+    want, _ = ora_micro.mel(synth_audio.to_f32(pcm16))
+    got = eng_micro.mel_pcm16(pcm16)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-3 * max(1.0, np.abs(want).max())
+    got32 = eng_micro.mel_f32(synth_audio.to_f32(pcm16))
+    assert np.array_equal(got, got32)  # int16 entry == the reference's /32768 host loop + f32 entry
+
+
+def test_mel_parity_128_bins_and_extremes(swb, ora):
+    path, _ = model_file("micro", seed=77, script_len=0)
+    # same micro model but with a 128-bin filterbank is not a valid hparam combo for conv1, so the
+    # 128-mel front end is exercised through a large-v3-shaped header on the smallest widths: tiny
+    # would be 80; instead check full-scale and silent inputs on the 80-bin model
+    e = swb.Engine(path, max_batch=2)
+    o = ora.Oracle(path)
+    for pcm16 in (np.full(16000 * 3, 32767, np.int16), np.full(16000 * 3, -32768, np.int16),
+                  np.zeros(16000 * 3, np.int16),
+                  (np.random.default_rng(1).integers(-32768, 32767, 16000 * 3)).astype(np.int16)):
+        want, _ = o.mel(synth_audio.to_f32(pcm16))
+        got = e.mel_pcm16(pcm16)
+        assert np.abs(got - want).max() <= 1e-3 * max(1.0, np.abs(want).max())
+    e.close()
+
+
+# ---------------------------------------------------------------- encoder / decoder stages
+def test_encoder_parity(eng_tiny, ora_tiny, ora, tiny_model):
+    pcm = synth_audio.to_f32(synth_audio.utterance(1, 0))
+    mel, _ = ora_tiny.mel(pcm)
+    wins = np.stack([mel[:, :3000], mel[:, 1000:4000], 0.5 * mel[:, :3000]])
+    got = eng_tiny.encode(wins)
+    ob = ora.Oracle(tiny_model[0], weight_round=True, act_round=ora.ACT_BF16)
+    for i in range(3):
+        want16 = ora_tiny.encode(wins[i])
+        assert rel(got[i], want16) < 2e-2          # vs whisper.cpp-mode numerics (f16 activations)
+        wantb = ob.encode(wins[i])
+        assert rel(got[i], wantb) < 1e-2           # vs the same bf16 rounding points
+        assert np.sqrt(((got[i] - want16) ** 2).mean()) / want16.std() < 5e-3
+
+
+def test_encoder_matches_hf_golden(eng_micro, swb, ora):
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "micro_hf.npz"))
+    args = ast.literal_eval(str(g["model_args"]))
+    path, info = model_file(args["size"], seed=args["seed"], script_len=args["script_len"])
+    # HF uses erf-GELU; the engine evaluates the tanh form whisper.cpp uses, so the bound is looser
+    o = ora.Oracle(path, act_round=ora.ACT_F32, gelu_erf=True)
+    c, i = [int(v) for v in g["pcm_config"]]
+    mel, _ = o.mel(synth_audio.to_f32(synth_audio.utterance(c, i)))
+    e = swb.Engine(path, max_batch=2)
+    enc = e.encode(mel[None, :, :3000])[0]
+    assert np.abs(enc[::15] - g["hf_enc_sub"]).max() / np.abs(g["hf_enc_sub"]).max() < 3e-2
+    logits = e.decode_logits(g["tokens"][None])[0]
+    assert (logits.argmax(1) == g["hf_argmax"]).all()
+    e.close()
+
+
+def test_decoder_logits_parity(eng_tiny, ora_tiny, tiny_model):
+    info = tiny_model[1]
+    sp = info["special"]
+    pcm = synth_audio.to_f32(synth_audio.utterance(1, 1))
+    mel, _ = ora_tiny.mel(pcm)
+    wins = np.stack([mel[:, :3000], mel[:, 500:3500]])
+    eng_tiny.encode(wins, want_output=False)
+    toks = np.array([sp["sot"], sp["sot"] + 1, sp["transcribe"]] + info["script"][:21], np.int32)
+    got = eng_tiny.decode_logits(np.stack([toks, toks]))
+    for w in range(2):
+        ora_tiny.encode(wins[w])
+        want = ora_tiny.decode(toks, 0)
+        assert rel(got[w], want) < 1e-2
+        assert (got[w].argmax(1) == want.argmax(1)).all()
+
+
+# ---------------------------------------------------------------- whole path
+def compare_results(got, want, p_tol=1e-2):
+    assert seg_ids(got) == seg_ids(want)
+    assert [(s["t0"], s["t1"], s["text"]) for s in got["segments"]] == \
+           [(s["t0"], s["t1"], s["text"]) for s in want["segments"]]
+    assert got["n_windows"] == want["n_windows"]
+    for sg, sw_ in zip(got["segments"], want["segments"]):
+        for a, b in zip(sg["tokens"], sw_["tokens"]):
+            assert abs(a["p"] - b["p"]) < p_tol
+            # tid (argmax over the timestamp probabilities) only matters when that mass is not
+            # negligible (upstream's thold_pt = 0.01); below it the argmax is rounding noise
+            if b["pt"] > 0.05 or b["id"] >= 50363:
+                assert a["tid"] == b["tid"]
+            assert (a["t0"], a["t1"]) == (b["t0"], b["t1"])
+
+
+@pytest.mark.parametrize("model", ["micro", "tiny"])
+def test_greedy_transcription_identical(request, model, swb, ora):
+    eng = request.getfixturevalue("eng_" + model)
+    o = request.getfixturevalue("ora_" + model)
+    clips = [synth_audio.utterance(3, i, seconds=s) for i, s in enumerate([30.0, 30.0, 12.0, 7.25, 30.0, 1.5, 21.0])]
+    pe = eng.default_params(0, **GREEDY)
+    po = o.default_params(0, **GREEDY)
+    got = eng.full_batch_pcm16(clips, pe)
+    for c, g in zip(clips, got):
+        compare_results(g, o.full(synth_audio.to_f32(c), po))
+
+
+def test_short_empty_and_silent_inputs(eng_micro, ora_micro):
+    pe = eng_micro.default_params(0, **GREEDY)
+    po = ora_micro.default_params(0, **GREEDY)
+    clips = [np.zeros(0, np.int16), np.zeros(800, np.int16), np.zeros(12000, np.int16),
+             np.zeros(16000 * 4, np.int16), synth_audio.utterance(3, 9, seconds=1.2)]
+    got = eng_micro.full_batch_pcm16(clips, pe)
+    for c, g in zip(clips, got):
+        compare_results(g, ora_micro.full(synth_audio.to_f32(c), po))
+    assert got[0]["segments"] == [] and got[1]["n_windows"] == 0 and got[2]["n_windows"] == 0
+
+
+def test_second_seek_window(swb, ora):
+    path, _ = model_file("micro", script_len=30, script_end_cs=2000, script_final_pair=True)
+    e = swb.Engine(path, max_batch=4)
+    o = ora.Oracle(path)
+    clip = synth_audio.utterance(1, 4)
+    got = e.full_batch_pcm16([clip, clip[: 16000 * 25]], e.default_params(0, **GREEDY))
+    po = o.default_params(0, **GREEDY)
+    for c, g in zip([clip, clip[: 16000 * 25]], got):
+        want = o.full(synth_audio.to_f32(c), po)
+        assert want["n_windows"] >= 2
+        compare_results(g, want)
+    e.close()
+
+
+def test_batch_invariance_and_idempotence(eng_tiny):
+    pe = eng_tiny.default_params(0, **GREEDY)
+    clip = synth_audio.utterance(3, 2)
+    other = synth_audio.utterance(3, 5, seconds=9.0)
+    alone = eng_tiny.full_batch_pcm16([clip], pe)[0]
+    again = eng_tiny.full_batch_pcm16([clip], pe)[0]
+    batch = eng_tiny.full_batch_pcm16([other, clip, clip, other, clip], pe)
+    assert alone == again                                   # same input twice: bit-identical results
+    assert seg_ids(batch[1]) == seg_ids(alone) == seg_ids(batch[2]) == seg_ids(batch[4])
+    assert batch[1] == batch[2]                             # two copies inside one batch
+    assert [s["text"] for s in batch[0]["segments"]] == [s["text"] for s in batch[3]["segments"]]
+
+
+def test_f32_entry_equals_pcm16_entry(eng_micro):
+    pe = eng_micro.default_params(0, **GREEDY)
+    clip = synth_audio.utterance(3, 6, seconds=14.0)
+    a = eng_micro.full_batch_pcm16([clip], pe)[0]
+    b = eng_micro.full_f32(synth_audio.to_f32(clip), pe)
+    assert a == b
+
+
+def test_more_utterances_than_max_batch(eng_micro, ora_micro):
+    pe = eng_micro.default_params(0, **GREEDY)
+    clips = [synth_audio.utterance(4, i, seconds=5.0 + (i % 4)) for i in range(19)]  # max_batch is 8
+    got = eng_micro.full_batch_pcm16(clips, pe)
+    po = ora_micro.default_params(0, **GREEDY)
+    for i in (0, 7, 8, 18):
+        compare_results(got[i], ora_micro.full(synth_audio.to_f32(clips[i]), po))
+
+
+def test_language_auto_detect_and_translate(eng_tiny, ora_tiny):
+    kw = dict(GREEDY)
+    kw["language"] = "auto"
+    clip = synth_audio.utterance(3, 7, seconds=8.0)
+    got = eng_tiny.full_batch_pcm16([clip], eng_tiny.default_params(0, **kw))[0]
+    want = ora_tiny.full(synth_audio.to_f32(clip), ora_tiny.default_params(0, **kw))
+    assert got["lang_id"] == want["lang_id"]
+    compare_results(got, want)
+    kw = dict(GREEDY, language="de", translate=1)
+    got = eng_tiny.full_batch_pcm16([clip], eng_tiny.default_params(0, **kw))[0]
+    want = ora_tiny.full(synth_audio.to_f32(clip), ora_tiny.default_params(0, **kw))
+    compare_results(got, want)
+
+
+def test_initial_prompt(eng_tiny, ora_tiny):
+    words = "".join(ora_tiny.token_str(i).decode() for i in (1500, 2500, 3500, 4500))
+    kw = dict(GREEDY, initial_prompt=words)
+    clip = synth_audio.utterance(3, 8, seconds=6.0)
+    got = eng_tiny.full_batch_pcm16([clip], eng_tiny.default_params(0, **kw))[0]
+    want = ora_tiny.full(synth_audio.to_f32(clip), ora_tiny.default_params(0, **kw))
+    assert seg_ids(got) == seg_ids(want)
+
+
+def test_beam_search_parity_margin_aware(eng_tiny, ora, tiny_model):
+    # upstream's beam search draws its candidates from the softmax with a seeded mt19937; both
+    # sides consume identical uniforms, so results agree unless a draw lands within the bf16
+    # probability error of a CDF boundary. The bf16-mode oracle removes most of that error.
+    ob = ora.Oracle(tiny_model[0], weight_round=True, act_round=ora.ACT_BF16)
+    kw = dict(language="en", temperature_inc=0.0, suppress_nst=1, beam_size=5)
+    clips = [synth_audio.utterance(3, 10 + i, seconds=s) for i, s in enumerate([30.0, 11.0, 18.0])]
+    got = eng_tiny.full_batch_pcm16(clips, eng_tiny.default_params(1, **kw))
+    same = 0
+    for c, g in zip(clips, got):
+        want = ob.full(synth_audio.to_f32(c), ob.default_params(1, **kw))
+        a, b = seg_ids(g), seg_ids(want)
+        assert len(a) == len(b)
+        agree = sum(x == y for x, y in zip(a, b)) / max(1, len(a))
+        assert agree >= 0.9
+        same += a == b
+    assert same >= 2
+
+
+def test_temperature_fallback_path_runs(swb, ora):
+    # a flat (unscripted) decoder fails the logprob threshold at T=0 and walks the temperature
+    # ladder; sampled tokens depend on rounding, so only the control flow is checked
+    path, _ = model_file("micro", seed=5, script_len=0)
+    e = swb.Engine(path, max_batch=2)
+    p = e.default_params(0, language="en", suppress_nst=1, logprob_thold=-0.7, temperature_inc=0.4, best_of=2)
+    r = e.full_batch_pcm16([synth_audio.utterance(3, 11, seconds=3.0)], p)[0]
+    assert r["n_windows"] >= 2  # the window was re-run at a higher temperature
+    e.close()
+
+
+def test_abort_callback_and_errors(swb, micro_model, eng_micro):
+    calls = []
+
+    @swb.ABORT_CB
+    def cb(_):
+        calls.append(1)
+        return 1 if len(calls) > 3 else 0
+    p = eng_micro.default_params(0, **GREEDY)
+    p.abort_callback = cb
+    with pytest.raises(RuntimeError) as ei:
+        eng_micro.full_batch_pcm16([synth_audio.utterance(3, 12)], p)
+    assert "abort" in str(ei.value)
+    with pytest.raises(RuntimeError):
+        swb.Engine("/nonexistent/model.bin")
+    bad = eng_micro.default_params(0, language="zz")
+    with pytest.raises(RuntimeError) as ei:
+        eng_micro.full_batch_pcm16([synth_audio.utterance(3, 12, seconds=2.0)], bad)
+    assert "language" in str(ei.value)
+    junk = os.path.join(os.path.dirname(micro_model[0]), "junk.bin")
+    open(junk, "wb").write(b"not a ggml file at all")
+    with pytest.raises(RuntimeError) as ei:
+        swb.Engine(junk)
+    assert "magic" in str(ei.value)
+    # the context is still usable after the failures
+    ok = eng_micro.full_batch_pcm16([synth_audio.utterance(3, 12, seconds=2.0)], eng_micro.default_params(0, **GREEDY))
+    assert ok[0]["n_windows"] == 1
+
+
+def test_config2_base_batch32_properties(swb, ora):
+    """BASELINE configs[1] at full size: Whisper base, 32 x 30 s windows in one batch. The oracle is
+    checked on two windows; the rest through size-independent properties (every window follows the
+    scripted transcript, duplicates inside the batch are bit-identical, segment times tile 0..30 s)."""
+    path, info = model_file("base", script_len=60)
+    e = swb.Engine(path, max_batch=32, max_beams=5)
+    clips = [synth_audio.utterance(2, i) for i in range(31)] + [synth_audio.utterance(2, 0)]
+    pe = e.default_params(0, **GREEDY)
+    got = e.full_batch_pcm16(clips, pe)
+    sp = info["special"]
+    script = info["script"]
+    kept = [t for i, t in enumerate(script[:-1]) if not (i > 0 and t >= sp["beg"] and script[i - 1] == t)]
+    n_follow = sum(seg_ids(g) == kept for g in got)
+    assert n_follow >= 31  # >= 99 % of segments token-identical is the north-star bar
+    assert got[0] == got[31]
+    for g in got:
+        assert g["segments"][0]["t0"] == 0 and g["segments"][-1]["t1"] == 3000
+    o = ora.Oracle(path)
+    po = o.default_params(0, **GREEDY)
+    for i in (3, 17):
+        compare_results(got[i], o.full(synth_audio.to_f32(clips[i]), po))
+    st = e.stats()
+    assert st["n_launches"] > 0 and st["n_windows"] == 32
+    e.close()

@@ -132,15 +132,16 @@ def make_vocab(n_base, seed):
     return toks[:n_base]
 
 
-def make_script(sp, n_tokens, seed, n_vocab_text, end_cs=3000, final_pair=True):
+def make_script(sp, n_tokens, seed, n_vocab_text, end_cs=3000, final_pair=False):
     """A valid timestamp-token transcript of n_tokens sampled tokens ending in EOT.
     end_cs: last timestamp in centiseconds/2 units (1500 = 30.00 s)."""
     rng = np.random.default_rng(seed)
     beg = sp["beg"]
     script = []
     n_seg = max(1, n_tokens // 14)
-    cuts = np.sort(rng.choice(np.arange(20, 1480), size=n_seg - 1, replace=False)) if n_seg > 1 else []
-    bounds = [0] + [int(c) for c in cuts] + [end_cs // 2 if end_cs <= 3000 else 1500]
+    last = min(end_cs // 2, 1500)
+    cuts = np.sort(rng.choice(np.arange(20, last - 20), size=n_seg - 1, replace=False)) if n_seg > 1 else []
+    bounds = [0] + [int(c) for c in cuts] + [last]
     bounds[-1] = min(bounds[-1], 1500)
     # budget: per segment 2 timestamps + text; final EOT
     n_text_total = n_tokens - 1 - 2 * n_seg
@@ -152,8 +153,8 @@ def make_script(sp, n_tokens, seed, n_vocab_text, end_cs=3000, final_pair=True):
         # ordinary text tokens (avoid the single-byte/non-speech region and specials)
         script.extend(int(t) for t in rng.integers(400, n_vocab_text, size=per[s]))
         script.append(beg + bounds[s + 1])
-    if not final_pair:
-        pass
+    if final_pair:  # transcript ends on a timestamp PAIR: upstream then seeks to it (second window)
+        script.append(script[-1])
     script.append(sp["eot"])
     return script
 
@@ -181,7 +182,8 @@ class GgmlWriter:
 
 
 def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, ln_f_gain=None,
-             script_end_cs=3000, w_std=0.02, emb_std=0.02, f32_all=False, verbose=False):
+             script_end_cs=3000, w_std=0.02, emb_std=0.02, f32_all=False, verbose=False,
+             script_final_pair=False):
     d, n_head, n_layer, n_mel, n_vocab = SIZES[size]
     if seed is None:
         seed = int.from_bytes(hashlib.sha256(size.encode()).digest()[:4], "little")
@@ -247,7 +249,8 @@ def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, l
     pos_emb = normal((N_TEXT_CTX, d), 0.01)
     script = []
     if script_len > 0:
-        script = make_script(sp, script_len, seed + 2, n_base - 1, end_cs=script_end_cs)
+        script = make_script(sp, script_len, seed + 2, n_base - 1, end_cs=script_end_cs,
+                             final_pair=script_final_pair)
         # first sampled position: 3 for multilingual ([sot, lang, transcribe]), 1 for .en ([sot])
         p0 = 3 if n_vocab >= 51865 else 1
         e16 = tok_emb.astype(np.float16).astype(np.float32)

@@ -8,7 +8,11 @@
 #include <math.h>
 #include <string.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <deque>
 #include <map>
 #include <random>
@@ -17,6 +21,10 @@
 
 namespace sw {
 namespace {
+
+double wall_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 constexpr int SR = 16000;
 constexpr int CHUNK_CS = 3000;  // 30 s in centiseconds
@@ -939,8 +947,11 @@ struct Run {
     else
       temps.push_back(p.temperature);
     for (int i = 0; i < n; ++i) SW_CHECK(n_samples[i] >= 0 && (n_samples[i] == 0 || pcm[i]), "utterance %d: null PCM", i);
+    const bool trace = getenv("SW_TRACE") != nullptr;
+    const double tf0 = wall_ms();
     if (setup_logit_cfg()) return -1;
     if (front_end(pcm, n_samples, n, is_f32)) return -1;
+    if (trace) fprintf(stderr, "[sw trace] front end of %d utterances: %.1f ms (wall)\n", n, wall_ms() - tf0);
     for (int i = 0; i < n; ++i) {
       out[i] = new sw_result();
       utts[i].res = out[i];
@@ -1003,10 +1014,13 @@ struct Run {
         wseek.push_back(w.seek);
         utts[w.utt].res->n_windows++;
       }
+      const double tw0 = wall_ms();
       if (finalize_windows(wutt, wseek)) return -1;
       if (engine_encode(e, (int)wins.size(), nullptr)) return -1;
+      const double tw1 = wall_ms();
       const int rc = decode_windows(wins);
       if (rc) return rc;
+      const double tw2 = wall_ms();
       for (auto& w : wins) {
         Utt& u = utts[w.utt];
         if (finish_window(w)) {
@@ -1015,6 +1029,9 @@ struct Run {
         }
         if (u.seek + 100 < u.seek_end) queue.push_back(Job{w.utt, 0});
       }
+      if (trace)
+        fprintf(stderr, "[sw trace] batch of %d windows: encode %.1f ms, decode %.1f ms, finish %.1f ms (wall)\n",
+                (int)wins.size(), tw1 - tw0, tw2 - tw1, wall_ms() - tw2);
     }
     return 0;
   }

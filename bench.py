@@ -185,6 +185,7 @@ def main():
     from tools import synth_audio
     eng = swb.Engine(path, device=local_rank, max_batch=args.batch, max_beams=5)
     params = eng.default_params(0, **SERVICE_PARAMS)  # greedy, best_of 5, temperature_inc 0.2 (defaults)
+    params.n_threads = min(16, os.cpu_count() or 4)  # host sequencer workers (Settings.n_threads knob)
     eng.set_kernel_timing(True)
 
     # ---- inputs: W windows of 30 s int16, pinned host copy + device copy

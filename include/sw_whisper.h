@@ -187,6 +187,15 @@ SW_API int sw_dev_gemm_bf16(const void* dA, const void* dB, void* dC, const floa
                             const float* d_residual, int M, int N, int K, int lda, int ldb, int ldc,
                             int flags, int block_n, void* stream);
 
+/* decoder-step kernels in isolation (tools/dev_decode_kernels.py): skinny weight-streaming GEMM
+ * (split <= 0: automatic) and the fused split-K-reduce + residual + LayerNorm */
+SW_API int sw_dev_skinny_gemm(const void* dX, const void* dW, int R, int N, int K, const float* d_bias,
+                              int gelu, void* d_out, float* d_partial, int split, void* stream);
+SW_API int sw_dev_skinny_split(int N, int K);
+SW_API int sw_dev_layer_norm(float* d_x, int rows, int d, const float* g, const float* b,
+                             void* d_out_bf16, const float* d_partial, int n_split, const float* d_bias,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,118 @@ layer_norm_kernel(float* __restrict__ x, int rows, int d, const float* __restric
     }
 }
 
+// Decoder-step variant: one CTA per row so that a 64-row step still spreads over 64 SMs
+// (the warp-per-row kernel above would use 16 CTAs). Thread t owns 8 consecutive elements.
+__global__ void __launch_bounds__(192)
+layer_norm_row_kernel(float* __restrict__ x, int d, const float* __restrict__ g, const float* __restrict__ b,
+                      bf16* __restrict__ out_bf16, float* __restrict__ out_f32, const float* __restrict__ partial,
+                      int n_split, int64_t split_stride, const float* __restrict__ add_bias) {
+  __shared__ float red[8];
+  const int row = blockIdx.x, t = threadIdx.x;
+  const int nch = d >> 3;
+  const bool act = t < nch;
+  float v[8];
+  float* xr = x + (int64_t)row * d + t * 8;
+  if (act) {
+    const float4 a0 = reinterpret_cast<const float4*>(xr)[0], a1 = reinterpret_cast<const float4*>(xr)[1];
+    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+    if (partial) {
+      if (add_bias) {
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(add_bias + t * 8));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(add_bias + t * 8) + 1);
+        v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w; v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
+      }
+      float4 p0[8], p1[8];
+#pragma unroll
+      for (int s = 0; s < 8; ++s)
+        if (s < n_split) {
+          const float4* p = reinterpret_cast<const float4*>(partial + s * split_stride + (int64_t)row * d + t * 8);
+          p0[s] = p[0];
+          p1[s] = p[1];
+        }
+#pragma unroll
+      for (int s = 0; s < 8; ++s)
+        if (s < n_split) {
+          v[0] += p0[s].x; v[1] += p0[s].y; v[2] += p0[s].z; v[3] += p0[s].w;
+          v[4] += p1[s].x; v[5] += p1[s].y; v[6] += p1[s].z; v[7] += p1[s].w;
+        }
+      for (int s = 8; s < n_split; ++s) {
+        const float4* p = reinterpret_cast<const float4*>(partial + s * split_stride + (int64_t)row * d + t * 8);
+        const float4 q0 = p[0], q1 = p[1];
+        v[0] += q0.x; v[1] += q0.y; v[2] += q0.z; v[3] += q0.w; v[4] += q1.x; v[5] += q1.y; v[6] += q1.z; v[7] += q1.w;
+      }
+      reinterpret_cast<float4*>(xr)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(xr)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
+  float sum = act ? ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])) : 0.f;
+  sum = warp_sum(sum);
+  if ((t & 31) == 0) red[t >> 5] = sum;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  const float mean = tot / (float)d;
+  __syncthreads();
+  float sq = 0.f;
+  if (act) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float c = v[i] - mean;
+      sq += c * c;
+    }
+  }
+  sq = warp_sum(sq);
+  if ((t & 31) == 0) red[t >> 5] = sq;
+  __syncthreads();
+  float tsq = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tsq += red[i];
+  const float scale = rsqrtf(tsq / (float)d + 1e-5f);
+  if (!act) return;
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + t * 8)), g1 = __ldg(reinterpret_cast<const float4*>(g + t * 8) + 1);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + t * 8)), b1 = __ldg(reinterpret_cast<const float4*>(b + t * 8) + 1);
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = (v[i] - mean) * scale * gg[i] + bb[i];
+  if (out_bf16) {
+    uint4 p;
+    p.x = pack_bf16x2(o[0], o[1]); p.y = pack_bf16x2(o[2], o[3]);
+    p.z = pack_bf16x2(o[4], o[5]); p.w = pack_bf16x2(o[6], o[7]);
+    reinterpret_cast<uint4*>(out_bf16 + (int64_t)row * d)[t] = p;
+  }
+  if (out_f32) {
+    reinterpret_cast<float4*>(out_f32 + (int64_t)row * d + t * 8)[0] = make_float4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<float4*>(out_f32 + (int64_t)row * d + t * 8)[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// out[r][:] = bf16(bias + sum_s partial[s][r][:])  (split-K reduce of a projection that is consumed as bf16)
+__global__ void __launch_bounds__(192)
+reduce_partials_kernel(const float* __restrict__ partial, int n_split, int64_t split_stride, int d,
+                       const float* __restrict__ bias, bf16* __restrict__ out) {
+  const int row = blockIdx.x, t = threadIdx.x;
+  if (t >= (d >> 3)) return;
+  float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (bias) {
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(bias + t * 8));
+    const float4 c1 = __ldg(reinterpret_cast<const float4*>(bias + t * 8) + 1);
+    v[0] = c0.x; v[1] = c0.y; v[2] = c0.z; v[3] = c0.w; v[4] = c1.x; v[5] = c1.y; v[6] = c1.z; v[7] = c1.w;
+  }
+  for (int s = 0; s < n_split; ++s) {
+    const float4* p = reinterpret_cast<const float4*>(partial + s * split_stride + (int64_t)row * d + t * 8);
+    const float4 q0 = p[0], q1 = p[1];
+    v[0] += q0.x; v[1] += q0.y; v[2] += q0.z; v[3] += q0.w; v[4] += q1.x; v[5] += q1.y; v[6] += q1.z; v[7] += q1.w;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  reinterpret_cast<uint4*>(out + (int64_t)row * d)[t] = o;
+}
+
 __global__ void zero_conv_pad_rows_kernel(bf16* buf, int d) {
   bf16* w = buf + (int64_t)blockIdx.x * (MEL_WIN_FRAMES + 2) * d;
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
@@ -109,8 +221,24 @@ int layer_norm(float* x, int rows, int d, const float* g, const float* b, bf16* 
                const float* add_bias, cudaStream_t stream) {
   if (rows <= 0) return 0;
   SW_CHECK(d % 128 == 0 && d <= 128 * LN_MAX_V4, "layer_norm: unsupported width %d", d);
+  if (rows <= 2048) {  // decoder step: spread the few rows over as many SMs
+    const int threads = ((d >> 3) + 31) / 32 * 32;
+    layer_norm_row_kernel<<<rows, threads, 0, stream>>>(x, d, g, b, out_bf16, out_f32, partial, n_split,
+                                                        split_stride, add_bias);
+    SW_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   layer_norm_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(x, rows, d, g, b, out_bf16, out_f32, partial,
                                                         n_split, split_stride, add_bias);
+  SW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int reduce_partials(const float* partial, int n_split, int64_t split_stride, int rows, int d,
+                    const float* bias, bf16* out, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  SW_CHECK(d % 8 == 0 && d <= 1536, "reduce_partials: unsupported width %d", d);
+  reduce_partials_kernel<<<rows, ((d >> 3) + 31) / 32 * 32, 0, stream>>>(partial, n_split, split_stride, d, bias, out);
   SW_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -57,7 +57,7 @@ static int engine_init(Engine* e, const char* path, const sw_ctx_params* p) {
   e->logits_ld = (hp.n_vocab + 3) / 4 * 4;
   if (e->dx.alloc(R * d) || e->dh.alloc(R * d) || e->dqkv.alloc(R * 3 * d) || e->datt.alloc(R * d) ||
       e->dq.alloc(R * d) || e->dff.alloc(R * 4 * d) || e->logits.alloc(R * e->logits_ld) ||
-      e->xa_ws.alloc(cross_attention_ws_floats((int)R, (int)d, hp.n_text_head)))
+      e->xa_ws.alloc(cross_attention_ws_floats((int)R, (int)d, hp.n_text_head)) || e->dpart.alloc(32 * R * d))
     return -1;
   e->n_pages = (int)(R * KV_MAX_PAGES + R);
   const size_t page_elems = (size_t)hp.n_text_layer * 2 * KV_PAGE * d;
@@ -207,62 +207,47 @@ int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_
                                   (size_t)e->max_rows * KV_MAX_PAGES * sizeof(int), cudaMemcpyHostToDevice, st));
   if (embed_tokens(m.tok_emb, m.dec_pos, e->d_tok.p, e->d_pos.p, R, d, e->dx.p, st)) return -1;
   const int64_t layer_stride = (int64_t)e->max_batch * 1500 * 2 * d;
+  // Weight-streaming GEMMs (skinny_gemm.cu). Projections that feed the residual stream or the
+  // cross-attention query are split along K; their f32 partial sums are folded in by the consumer
+  // (the fused LayerNorm adds bias + partials into x; cross_attention reduces its query on load).
+  const int sp_d = skinny_split_for(d, d), sp_ff = skinny_split_for(d, 4 * d);
+  const int64_t pstride = (int64_t)R * d;
+  float* part = e->dpart.p;
+  const float* pend_bias = nullptr;  // bias of the FC2 partials still to be folded into x
+  int pend_split = 0;
   for (int l = 0; l < L; ++l) {
     const DecLayerW& w = m.dec[l];
-    if (layer_norm(e->dx.p, R, d, w.ln1.g, w.ln1.b, e->dh.p, nullptr, nullptr, 0, 0, nullptr, st)) return -1;
-    {
-      GemmArgs a;
-      a.A = e->dh.p; a.lda = d; a.B = w.wqkv; a.ldb = d; a.C = e->dqkv.p; a.ldc = 3 * d;
-      a.bias = w.bqkv; a.M = R; a.N = 3 * d; a.K = d;
-      GEMM(a);
-    }
+    if (layer_norm(e->dx.p, R, d, w.ln1.g, w.ln1.b, e->dh.p, nullptr, pend_split ? part : nullptr, pend_split,
+                   pstride, pend_bias, st))
+      return -1;
+    if (skinny_gemm(e->dh.p, d, w.wqkv, R, 3 * d, d, w.bqkv, 0, e->dqkv.p, 3 * d, nullptr, 1, st)) return -1;
     if (kv_append(e->dqkv.p, e->d_rows.p, R, d, e->kv_pool.p, e->d_page_table.p, l, L, st)) return -1;
     if (self_attention(e->dqkv.p, e->d_rows.p, R, d, hp.n_text_head, e->kv_pool.p, e->d_page_table.p, l, L,
                        e->datt.p, st))
       return -1;
-    {
-      GemmArgs a;
-      a.A = e->datt.p; a.lda = d; a.B = w.wo; a.ldb = d; a.C = e->dx.p; a.ldc = d;
-      a.bias = w.bo; a.residual = e->dx.p; a.ldr = d; a.M = R; a.N = d; a.K = d; a.flags = GEMM_OUT_F32;
-      GEMM(a);
-    }
-    if (layer_norm(e->dx.p, R, d, w.lnx.g, w.lnx.b, e->dh.p, nullptr, nullptr, 0, 0, nullptr, st)) return -1;
-    {
-      GemmArgs a;
-      a.A = e->dh.p; a.lda = d; a.B = w.wxq; a.ldb = d; a.C = e->dq.p; a.ldc = d;
-      a.bias = w.bxq; a.M = R; a.N = d; a.K = d;
-      GEMM(a);
-    }
+    if (skinny_gemm(e->datt.p, d, w.wo, R, d, d, nullptr, 0, nullptr, 0, part, sp_d, st)) return -1;
+    if (layer_norm(e->dx.p, R, d, w.lnx.g, w.lnx.b, e->dh.p, nullptr, part, sp_d, pstride, w.bo, st)) return -1;
+    if (skinny_gemm(e->dh.p, d, w.wxq, R, d, d, nullptr, 0, nullptr, 0, part, sp_d, st)) return -1;
+    if (reduce_partials(part, sp_d, pstride, R, d, w.bxq, e->dq.p, st)) return -1;
     if (e->kernel_timing) SW_CUDA_CHECK(cudaEventRecord(e->xa_ev[2 * l], st));
-    if (cross_attention(e->dq.p, e->cross_kv.p + l * layer_stride, e->d_grp_win.p, e->d_grp_start.p,
-                        e->d_grp_count.p, n_groups, max_count, R, 1500, d, hp.n_text_head, e->xa_ws.p,
-                        e->datt.p, st))
+    if (cross_attention(e->dq.p, e->cross_kv.p + l * layer_stride, e->d_grp_win.p,
+                        e->d_grp_start.p, e->d_grp_count.p, n_groups, max_count, R, 1500, d, hp.n_text_head,
+                        e->xa_ws.p, e->datt.p, st))
       return -1;
     if (e->kernel_timing) SW_CUDA_CHECK(cudaEventRecord(e->xa_ev[2 * l + 1], st));
-    {
-      GemmArgs a;
-      a.A = e->datt.p; a.lda = d; a.B = w.wxo; a.ldb = d; a.C = e->dx.p; a.ldc = d;
-      a.bias = w.bxo; a.residual = e->dx.p; a.ldr = d; a.M = R; a.N = d; a.K = d; a.flags = GEMM_OUT_F32;
-      GEMM(a);
-    }
-    if (layer_norm(e->dx.p, R, d, w.ln2.g, w.ln2.b, e->dh.p, nullptr, nullptr, 0, 0, nullptr, st)) return -1;
-    {
-      GemmArgs a;
-      a.A = e->dh.p; a.lda = d; a.B = w.w1; a.ldb = d; a.C = e->dff.p; a.ldc = 4 * d;
-      a.bias = w.b1; a.M = R; a.N = 4 * d; a.K = d; a.flags = GEMM_GELU;
-      GEMM(a);
-    }
-    {
-      GemmArgs a;
-      a.A = e->dff.p; a.lda = 4 * d; a.B = w.w2; a.ldb = 4 * d; a.C = e->dx.p; a.ldc = d;
-      a.bias = w.b2; a.residual = e->dx.p; a.ldr = d; a.M = R; a.N = d; a.K = 4 * d; a.flags = GEMM_OUT_F32;
-      GEMM(a);
-    }
-    e->times.n_launches += 7;
+    if (skinny_gemm(e->datt.p, d, w.wxo, R, d, d, nullptr, 0, nullptr, 0, part, sp_d, st)) return -1;
+    if (layer_norm(e->dx.p, R, d, w.ln2.g, w.ln2.b, e->dh.p, nullptr, part, sp_d, pstride, w.bxo, st)) return -1;
+    if (skinny_gemm(e->dh.p, d, w.w1, R, 4 * d, d, w.b1, 1, e->dff.p, 4 * d, nullptr, 1, st)) return -1;
+    if (skinny_gemm(e->dff.p, 4 * d, w.w2, R, d, 4 * d, nullptr, 0, nullptr, 0, part, sp_ff, st)) return -1;
+    pend_bias = w.b2;
+    pend_split = sp_ff;
+    e->times.n_launches += 14;
   }
   e->times.n_launches += 1;
   if (want_logits || n_lrows > 0) {
-    if (layer_norm(e->dx.p, R, d, m.dec_ln.g, m.dec_ln.b, e->dh.p, nullptr, nullptr, 0, 0, nullptr, st)) return -1;
+    if (layer_norm(e->dx.p, R, d, m.dec_ln.g, m.dec_ln.b, e->dh.p, nullptr, pend_split ? part : nullptr,
+                   pend_split, pstride, pend_bias, st))
+      return -1;
     GemmArgs a;
     a.A = e->dh.p; a.lda = d; a.B = m.tok_emb; a.ldb = d; a.C = e->logits.p; a.ldc = e->logits_ld;
     a.M = R; a.N = hp.n_vocab; a.K = d; a.flags = GEMM_OUT_F32;

@@ -82,7 +82,7 @@ struct Engine {
   DevBuf<float> x;
   DevBuf<bf16> cross_kv;        // [n_text_layer][max_batch*1500][2d]
   // ---- decoder
-  DevBuf<float> dx, logits, xa_ws;
+  DevBuf<float> dx, logits, xa_ws, dpart;  // dpart: split-K partial sums [split][R][d]
   DevBuf<bf16> dh, dqkv, datt, dq, dff;
   DevBuf<bf16> kv_pool;
   int n_pages = 0;

@@ -39,6 +39,10 @@ struct GemmArgs {
 // Enqueue on `stream`. Returns 0 or -1 (see sw_last_error()).
 int gemm_bf16_tn(const GemmArgs& args, cudaStream_t stream);
 
+// 2-D bf16 tensor map {inner, rows} with a {box_inner (=64), box_rows} box and 128B swizzle; map_out is a CUtensorMap*
+int make_tma_map_2d_bf16(void* map_out, const void* base, int64_t inner, int64_t rows, int64_t ld_elems,
+                         int box_inner, int box_rows);
+
 // FLOPs actually requested (2*M*N*K*batch) - for roofline accounting.
 inline double gemm_flops(const GemmArgs& a) {
   return 2.0 * a.M * (double)a.N * a.K * a.batch;

@@ -372,6 +372,22 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
+int make_tma_map_2d_bf16(void* map_out, const void* base, int64_t inner, int64_t rows, int64_t ld_elems,
+                         int box_inner, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  SW_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  SW_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld_elems * 2) % 16 == 0, "TMA operand not 16B aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(static_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SW_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d) failed: %d", (int)r);
+  return 0;
+}
+
 int gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
   SW_CHECK(a.M > 0 && a.N > 0 && a.K > 0 && a.batch > 0, "gemm: empty problem");
   SW_CHECK(a.A && a.B && a.C, "gemm: null operand");

@@ -51,6 +51,9 @@ int signal_energy(const void* pcm, int is_f32, const MelUtt* d_utts, int n_utts,
 int layer_norm(float* x, int rows, int d, const float* g, const float* b, bf16* out_bf16,
                float* out_f32, const float* partial, int n_split, int64_t split_stride,
                const float* add_bias, cudaStream_t stream);
+// out[r][:] = bf16(bias + sum_s partial[s][r][:])
+int reduce_partials(const float* partial, int n_split, int64_t split_stride, int rows, int d,
+                    const float* bias, bf16* out, cudaStream_t stream);
 // zero the pad rows (0 and 3001) of a [n_win][3002][d] bf16 buffer
 int zero_conv_pad_rows(bf16* buf, int n_win, int d, cudaStream_t stream);
 // x[r][:] = tok_emb[tok[r]][:] + pos_emb[pos[r]][:]
@@ -90,6 +93,12 @@ size_t cross_attention_ws_floats(int R, int d, int n_head);
 int cross_attention(const bf16* q, const bf16* kv, const int* d_grp_win, const int* d_grp_start,
                     const int* d_grp_count, int n_groups, int max_count, int R, int T, int d,
                     int n_head, float* ws, bf16* out, cudaStream_t stream);
+
+// weight-streaming GEMM for <= 64-row blocks (skinny_gemm.cu): out = X . W^T
+//   split == 1: out bf16 [R][ldo] = act(acc + bias);   split > 1: partial f32 [split][R][N] (raw sums)
+int skinny_split_for(int N, int K);
+int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, const float* bias, int gelu,
+                bf16* out, int ldo, float* partial, int split, cudaStream_t stream);
 
 // logit rules + log-softmax + pick (whisper_process_logits + whisper_sample_token)
 struct LogitRow {        // per-row rule state, built by the host sequencer

@@ -12,10 +12,12 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <deque>
 #include <map>
 #include <random>
+#include <thread>
 
 #include "host_common.h"
 
@@ -991,8 +993,61 @@ struct Run {
       if (u.seek + 100 >= u.seek_end) continue;
       queue.push_back(Job{i, 0});
     }
+    // Host post-processing of a finished batch (ranking, segments, token-level timestamps) runs on
+    // worker threads while the GPU already encodes / decodes the next batch of other utterances.
+    struct Pending {
+      std::vector<Window> wins;
+      std::vector<char> rerun;
+      std::thread th;
+      bool active = false, failed = false;
+      ~Pending() {
+        if (th.joinable()) th.join();
+      }
+    } pend;
+    const int n_workers = std::max(1, std::min(p.n_threads > 0 ? p.n_threads : 4, 64));
+    auto start_finish = [&](std::vector<Window>&& ws) {
+      pend.wins = std::move(ws);
+      pend.rerun.assign(pend.wins.size(), 0);
+      pend.active = true;
+      pend.th = std::thread([this, &pend, n_workers] {
+        std::atomic<int> next{0};
+        auto work = [&] {
+          try {
+            for (;;) {
+              const int i = next.fetch_add(1);
+              if (i >= (int)pend.wins.size()) break;
+              pend.rerun[i] = finish_window(pend.wins[i]) ? 1 : 0;
+            }
+          } catch (...) {
+            pend.failed = true;
+          }
+        };
+        std::vector<std::thread> pool;
+        const int nt = std::min<int>(n_workers, (int)pend.wins.size());
+        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+        work();
+        for (auto& t : pool) t.join();
+      });
+    };
+    auto collect = [&]() -> int {
+      if (!pend.active) return 0;
+      pend.th.join();
+      pend.active = false;
+      SW_CHECK(!pend.failed, "out of host memory while building results");
+      for (size_t i = 0; i < pend.wins.size(); ++i) {
+        const Window& w = pend.wins[i];
+        const Utt& u = utts[w.utt];
+        if (pend.rerun[i]) queue.push_back(Job{w.utt, w.temp_idx + 1});
+        else if (u.seek + 100 < u.seek_end) queue.push_back(Job{w.utt, 0});
+      }
+      return 0;
+    };
     std::vector<Window> wins;
-    while (!queue.empty()) {
+    while (true) {
+      if (queue.empty()) {
+        if (collect()) return -1;
+        if (queue.empty()) break;
+      }
       if (aborted()) {
         set_last_error("aborted by callback");
         return -6;
@@ -1021,17 +1076,11 @@ struct Run {
       const int rc = decode_windows(wins);
       if (rc) return rc;
       const double tw2 = wall_ms();
-      for (auto& w : wins) {
-        Utt& u = utts[w.utt];
-        if (finish_window(w)) {
-          queue.push_back(Job{w.utt, w.temp_idx + 1});
-          continue;
-        }
-        if (u.seek + 100 < u.seek_end) queue.push_back(Job{w.utt, 0});
-      }
+      if (collect()) return -1;  // at most one batch of host post-processing in flight
       if (trace)
-        fprintf(stderr, "[sw trace] batch of %d windows: encode %.1f ms, decode %.1f ms, finish %.1f ms (wall)\n",
+        fprintf(stderr, "[sw trace] batch of %d windows: encode %.1f ms, decode %.1f ms, wait for previous finish %.1f ms (wall)\n",
                 (int)wins.size(), tw1 - tw0, tw2 - tw1, wall_ms() - tw2);
+      start_finish(std::move(wins));
     }
     return 0;
   }

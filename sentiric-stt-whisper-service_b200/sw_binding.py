@@ -67,7 +67,7 @@ EXPORTS = [
     "sw_result_segment_speaker_turn_next", "sw_result_n_tokens", "sw_result_token_data",
     "sw_result_lang_id", "sw_result_n_decode_steps", "sw_result_n_windows", "sw_result_free",
     "sw_ctx_get_stats", "sw_ctx_set_kernel_timing", "sw_mel_pcm16", "sw_mel_f32", "sw_encode", "sw_decode_logits",
-    "sw_dev_gemm_bf16"]
+    "sw_dev_gemm_bf16", "sw_dev_skinny_gemm", "sw_dev_skinny_split", "sw_dev_layer_norm"]
 
 _lib = None
 

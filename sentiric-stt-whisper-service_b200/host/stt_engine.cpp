@@ -1,0 +1,312 @@
+// See stt_engine.h. Line references are to /root/reference/src/stt_engine.cpp, whose observable
+// behaviour each block reproduces.
+#include "stt_engine.h"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+
+#include "model_manager.h"
+#include "text_filters.h"
+
+using Clock = std::chrono::high_resolution_clock;
+
+struct SttEngine::Request {
+  const float* pcm = nullptr;      // exactly one of pcm / pcm16 is set
+  const int16_t* pcm16 = nullptr;
+  int n = 0;
+  sw_full_params params;
+  std::string language, prompt;   // own the strings params points at
+  std::function<bool()> abort_fn;
+  sw_result* result = nullptr;
+  int rc = 0;
+  std::string error;
+  bool done = false;
+  std::mutex m;
+  std::condition_variable cv;
+  // requests run in one device pass only if every decode setting is identical
+  bool compatible(const Request& o) const {
+    const sw_full_params &a = params, &b = o.params;
+    return !abort_fn && !o.abort_fn && (pcm16 != nullptr) == (o.pcm16 != nullptr) && a.strategy == b.strategy &&
+           a.beam_size == b.beam_size && a.best_of == b.best_of && a.temperature == b.temperature &&
+           a.translate == b.translate && a.tdrz_enable == b.tdrz_enable && language == o.language &&
+           prompt == o.prompt;
+  }
+};
+
+static int abort_trampoline(void* user) {  // stt_engine.cpp:17-23
+  auto* fn = static_cast<std::function<bool()>*>(user);
+  return (fn && *fn && (*fn)()) ? 1 : 0;
+}
+
+SttEngine::SttEngine(const Settings& settings) : settings_(settings) {
+  // :26-34 - load the model or throw
+  const std::string model_path = settings_.model_dir + "/" + settings_.model_filename;
+  const int max_beams = std::max(1, std::min(8, std::max(settings_.beam_size, settings_.best_of)));
+  ctx_ = ModelManager::load_to_device(settings_, model_path, max_beams);
+  if (!ctx_) {
+    fprintf(stderr, "[stt_engine] %s\n", sw_last_error());
+    throw std::runtime_error("Whisper model initialization failed");
+  }
+  // :36-42 - the state pool becomes an admission counter
+  free_slots_ = std::max(1, settings_.parallel_requests);
+  // :44-52 - Silero VAD is a CPU-side pre-gate outside the hot path: not loaded
+  dispatcher_ = std::thread([this] { dispatcher_loop(); });
+}
+
+SttEngine::~SttEngine() {
+  {
+    std::lock_guard<std::mutex> lk(q_mutex_);
+    stopping_ = true;
+  }
+  q_cv_.notify_all();
+  if (dispatcher_.joinable()) dispatcher_.join();
+  if (ctx_) sw_ctx_destroy(ctx_);
+}
+
+bool SttEngine::is_ready() const { return ctx_ != nullptr; }
+
+void SttEngine::acquire_slot() {  // :63-79
+  std::unique_lock<std::mutex> lock(pool_mutex_);
+  const bool ok = pool_cv_.wait_for(lock, std::chrono::milliseconds(settings_.request_queue_timeout_ms),
+                                    [this] { return free_slots_ > 0; });
+  if (!ok) throw EngineBusyException("Server is busy (Queue timeout)");
+  --free_slots_;
+}
+
+void SttEngine::release_slot() {  // :81-85
+  {
+    std::lock_guard<std::mutex> lock(pool_mutex_);
+    ++free_slots_;
+  }
+  pool_cv_.notify_one();
+}
+
+void SttEngine::dispatcher_loop() {
+  while (true) {
+    std::vector<Request*> batch;
+    {
+      std::unique_lock<std::mutex> lk(q_mutex_);
+      q_cv_.wait(lk, [this] { return stopping_ || !queue_.empty(); });
+      if (stopping_ && queue_.empty()) return;
+      if (settings_.batch_window_us > 0 && (int)queue_.size() < settings_.max_batch) {
+        // give concurrent callers a moment to join this device pass
+        q_cv_.wait_for(lk, std::chrono::microseconds(settings_.batch_window_us),
+                       [this] { return stopping_ || (int)queue_.size() >= settings_.max_batch; });
+      }
+      Request* head = queue_.front();
+      queue_.pop_front();
+      batch.push_back(head);
+      for (auto it = queue_.begin(); it != queue_.end() && (int)batch.size() < 4 * settings_.max_batch;) {
+        if (head->compatible(**it)) {
+          batch.push_back(*it);
+          it = queue_.erase(it);
+        } else {
+          ++it;
+        }
+      }
+    }
+    const int n = (int)batch.size();
+    std::vector<int> lens(n);
+    std::vector<sw_result*> res(n, nullptr);
+    for (int i = 0; i < n; ++i) lens[i] = batch[i]->n;
+    int rc;
+    if (batch[0]->pcm16) {
+      std::vector<const int16_t*> ptrs(n);
+      for (int i = 0; i < n; ++i) ptrs[i] = batch[i]->pcm16;
+      rc = sw_full_batch_pcm16(ctx_, &batch[0]->params, ptrs.data(), lens.data(), n, res.data());
+    } else {
+      std::vector<const float*> ptrs(n);
+      for (int i = 0; i < n; ++i) ptrs[i] = batch[i]->pcm;
+      rc = sw_full_batch_f32(ctx_, &batch[0]->params, ptrs.data(), lens.data(), n, res.data());
+    }
+    const std::string err = rc ? sw_last_error() : "";
+    ++batches_run_;
+    requests_batched_ += n;
+    for (int i = 0; i < n; ++i) {
+      Request* r = batch[i];
+      {
+        std::lock_guard<std::mutex> lk(r->m);
+        r->rc = rc;
+        r->error = err;
+        r->result = res[i];
+        r->done = true;
+      }
+      r->cv.notify_one();
+    }
+  }
+}
+
+std::vector<TranscriptionResult> SttEngine::transcribe_pcm16(const std::vector<int16_t>& pcm16, int input_sample_rate,
+                                                             const RequestOptions& options,
+                                                             PerformanceMetrics* out_metrics) {
+  // :117-125 converts to float on the host; here the int16 samples go to the device as they are
+  // and the /32768 happens in the front-end kernel's load.
+  const auto t_start = Clock::now();
+  if (input_sample_rate != 16000) {
+    std::vector<float> f(pcm16.size());
+    for (size_t i = 0; i < pcm16.size(); ++i) f[i] = static_cast<float>(pcm16[i]) / 32768.0f;
+    return transcribe(f, input_sample_rate, options, out_metrics);
+  }
+  return run_request(nullptr, pcm16.size(), pcm16.data(), options, out_metrics, t_start);
+}
+
+std::vector<TranscriptionResult> SttEngine::transcribe(const std::vector<float>& pcmf32, int input_sample_rate,
+                                                       const RequestOptions& options,
+                                                       PerformanceMetrics* out_metrics) {
+  const auto t_start = Clock::now();
+  if (input_sample_rate != 16000) {
+    // :138-145 resamples with libsamplerate (SRC_SINC_FASTEST); that codec-side step is outside the
+    // hot path and the library is not available: refuse loudly.
+    throw std::invalid_argument("SttEngine: only 16 kHz input is supported by this build (got " +
+                                std::to_string(input_sample_rate) + " Hz)");
+  }
+  return run_request(pcmf32.data(), pcmf32.size(), nullptr, options, out_metrics, t_start);
+}
+
+std::vector<TranscriptionResult> SttEngine::run_request(const float* pcm, size_t pcm_size, const int16_t* pcm16,
+                                                        const RequestOptions& options,
+                                                        PerformanceMetrics* out_metrics, Clock::time_point t_start) {
+  if (!ctx_) return {};                                          // :132
+  if (options.should_abort && options.should_abort()) return {};  // :133
+
+  // :153-167 - too short to process
+  const size_t min_samples = static_cast<size_t>((settings_.vad_ms_min_duration * 16000) / 1000);
+  if (pcm_size < min_samples) {
+    if (out_metrics) {
+      out_metrics->queue_time_ms = 0;
+      out_metrics->processing_time_ms = 0;
+      out_metrics->token_count = 0;
+    }
+    return {};
+  }
+  // :169-194 - the Silero VAD pre-gate is not part of this build (see constructor); enable_vad is
+  // honoured as "no gate", which is also what the deployment runs with.
+
+  acquire_slot();  // throws EngineBusyException after request_queue_timeout_ms (:197-198)
+  struct SlotGuard {
+    SttEngine& e;
+    ~SlotGuard() { e.release_slot(); }
+  } guard{*this};
+  const auto t_acquired = Clock::now();
+
+  SpeakerClusterer clusterer(settings_.cluster_threshold);  // :202
+
+  // :204-243 - parameter mapping
+  const int active_beam = options.beam_size >= 0 ? options.beam_size : settings_.beam_size;
+  const float active_temp = options.temperature >= 0.0f ? options.temperature : settings_.temperature;
+  const int active_best_of = options.best_of >= 0 ? options.best_of : settings_.best_of;
+  const int strategy = active_beam > 1 ? 1 : 0;
+  Request req;
+  req.pcm = pcm;
+  req.pcm16 = pcm16;
+  req.n = static_cast<int>(pcm_size);
+  req.params = sw_full_default_params(strategy);
+  req.abort_fn = options.should_abort;
+  if (req.abort_fn) {
+    req.params.abort_callback = abort_trampoline;
+    req.params.abort_callback_user_data = &req.abort_fn;
+  }
+  req.params.token_timestamps = 1;
+  req.params.suppress_nst = settings_.suppress_nst ? 1 : 0;
+  req.params.no_speech_thold = settings_.no_speech_threshold;
+  req.params.translate = options.translate ? 1 : 0;
+  req.params.tdrz_enable = options.enable_diarization ? 1 : 0;
+  req.language = options.language.empty() ? settings_.language : options.language;
+  req.params.language = req.language.c_str();
+  req.prompt = options.prompt;
+  req.params.initial_prompt = req.prompt.empty() ? nullptr : req.prompt.c_str();
+  req.params.temperature = active_temp;
+  if (strategy == 1) req.params.beam_size = active_beam;
+  else req.params.best_of = active_best_of;
+  req.params.entropy_thold = 2.40f;
+  req.params.logprob_thold = settings_.logprob_threshold;
+  req.params.n_threads = settings_.n_threads;
+
+  // :245-246 - whisper_full_with_state, here: join the next device pass
+  {
+    std::lock_guard<std::mutex> lk(q_mutex_);
+    queue_.push_back(&req);
+  }
+  q_cv_.notify_all();
+  {
+    std::unique_lock<std::mutex> lk(req.m);
+    req.cv.wait(lk, [&] { return req.done; });
+  }
+  const auto t_end = Clock::now();
+  if (out_metrics) {  // :250-256
+    out_metrics->queue_time_ms = std::chrono::duration<double, std::milli>(t_acquired - t_start).count();
+    out_metrics->processing_time_ms = std::chrono::duration<double, std::milli>(t_end - t_acquired).count();
+    out_metrics->token_count = 0;
+  }
+
+  std::vector<TranscriptionResult> results;
+  if (req.rc != 0 || !req.result) {  // :341-346 - log and return nothing
+    if (!(options.should_abort && options.should_abort()))
+      fprintf(stderr, "[stt_engine] Whisper processing failed: %d (%s)\n", req.rc, req.error.c_str());
+    return results;
+  }
+  struct ResultGuard {
+    sw_result* r;
+    ~ResultGuard() { sw_result_free(r); }
+  } rguard{req.result};
+
+  const float kMinAvgTokenProb = 0.40f;  // :264
+  const int eot = sw_token_eot(ctx_);
+  const int n_segments = sw_result_n_segments(req.result);  // :261
+  // prosody works on float samples: convert lazily, only the slices that are analysed
+  std::vector<float> slice;
+  for (int i = 0; i < n_segments; ++i) {
+    const char* text_c = sw_result_segment_text(req.result, i);
+    const std::string text = text_c ? text_c : "";
+    if (sentiric::utils::is_hallucination(text)) continue;  // :272-278
+    const int64_t t0 = sw_result_segment_t0(req.result, i), t1 = sw_result_segment_t1(req.result, i);
+    const bool turn = sw_result_segment_speaker_turn_next(req.result, i) != 0;
+
+    std::vector<TokenData> tokens;  // :285-296
+    double total_prob = 0.0;
+    int valid = 0;
+    const int n_tokens = sw_result_n_tokens(req.result, i);
+    for (int j = 0; j < n_tokens; ++j) {
+      const sw_token_data d = sw_result_token_data(req.result, i, j);
+      if (d.id >= eot) continue;
+      tokens.push_back({std::string(sw_token_to_str(ctx_, d.id)), d.p, d.t0, d.t1});
+      total_prob += d.p;
+      ++valid;
+    }
+    if (out_metrics) out_metrics->token_count += valid;
+    const float avg_prob = valid > 0 ? static_cast<float>(total_prob / valid) : 0.0f;
+    if (avg_prob < kMinAvgTokenProb && valid > 0) continue;  // :300-311
+
+    // :313-334 - slice the PCM of the segment for prosody + speaker id
+    int64_t s0 = static_cast<int64_t>((static_cast<double>(t0) / 100.0) * 16000.0);
+    int64_t s1 = static_cast<int64_t>((static_cast<double>(t1) / 100.0) * 16000.0);
+    s0 = std::max<int64_t>(0, std::min<int64_t>(s0, (int64_t)pcm_size));
+    s1 = std::max<int64_t>(s0, std::min<int64_t>(s1, (int64_t)pcm_size));
+    const size_t seg = static_cast<size_t>(s1 - s0);
+    AffectiveTags pros;
+    std::string spk = "?";
+    if (seg < 160) {
+      pros = prosody_fn_(nullptr, 0, 16000, options.prosody_opts);
+    } else {
+      const float* p = nullptr;
+      if (pcm) {
+        p = pcm + s0;
+      } else {
+        slice.resize(seg);
+        for (size_t k = 0; k < seg; ++k) slice[k] = static_cast<float>(pcm16[s0 + k]) / 32768.0f;
+        p = slice.data();
+      }
+      pros = prosody_fn_(p, seg, 16000, options.prosody_opts);
+      bool any = false;
+      for (float v : pros.speaker_vec) any = any || v != 0.0f;
+      if (!pros.speaker_vec.empty() && any) spk = clusterer.assign_or_add(pros.speaker_vec);
+    }
+    results.push_back({text, req.language, avg_prob, t0, t1, turn, tokens, valid, pros.gender_proxy,
+                       pros.emotion_proxy, pros.arousal, pros.valence, pros, spk});  // :336-339
+  }
+  return results;
+}

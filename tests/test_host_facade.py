@@ -1,0 +1,68 @@
+"""The C++ SttEngine / ModelManager facade above the C ABI (reference: src/stt_engine.{h,cpp})."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import PKG, model_file
+from tools import synth_audio
+
+HOST = os.path.join(PKG, "host")
+
+
+def build_host():
+    subprocess.check_call(["make", "-s", "-C", PKG])
+    subprocess.check_call(["make", "-s", "-C", HOST])
+
+
+def test_host_selftest_cpu(tmp_path):
+    build_host()
+    r = subprocess.run([os.path.join(HOST, "build", "host_selftest"), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0 and "HOST_SELFTEST_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_facade_headers_keep_the_reference_api():
+    src = open(os.path.join(HOST, "stt_engine.h")).read()
+    for needle in ("explicit SttEngine(const Settings& settings);", "bool is_ready() const;",
+                   "const Settings& get_settings() const", "struct PerformanceMetrics",
+                   "std::vector<TranscriptionResult> transcribe(const std::vector<float>& pcmf32, int input_sample_rate,",
+                   "std::vector<TranscriptionResult> transcribe_pcm16(const std::vector<int16_t>& pcm16, int input_sample_rate,",
+                   "class EngineBusyException : public std::runtime_error", "std::function<bool()> should_abort"):
+        assert needle in src, needle
+
+
+@pytest.mark.gpu
+def test_facade_matches_c_abi_and_batches_concurrent_callers(swb, tmp_path):
+    build_host()
+    path, info = model_file("tiny")
+    clip = synth_audio.utterance(3, 21, seconds=16.0)
+    raw = tmp_path / "clip.raw"
+    clip.tofile(raw)
+    r = subprocess.run([os.path.join(HOST, "build", "stt_cli"), os.path.dirname(path), os.path.basename(path),
+                        str(raw), "3", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    outs = [json.loads(l) for l in r.stdout.strip().splitlines()]
+    assert len(outs) == 3
+    assert outs[0]["batches_run"] < 3  # the three concurrent callers shared device passes
+    eng = swb.Engine(path, max_batch=8)
+    p = eng.default_params(0, language="en", token_timestamps=1, suppress_nst=1, no_speech_thold=0.85,
+                           logprob_thold=-0.7, entropy_thold=2.4, temperature=0.0, best_of=5)
+    want = eng.full_batch_pcm16([clip], p)[0]
+    eot = eng.info.token_eot
+    segs = []
+    for s in want["segments"]:
+        toks = [t for t in s["tokens"] if t["id"] < eot]
+        if toks and np.mean([t["p"] for t in toks]) < 0.40:
+            continue
+        segs.append((s["t0"], s["t1"], [(eng.token_str(t["id"]).decode("utf-8", "replace"), t["t0"], t["t1"]) for t in toks]))
+    for o in outs:
+        got = [(s["t0"], s["t1"], [(t[0], t[2], t[3]) for t in s["tokens"]]) for s in o["segments"]]
+        assert [(a, b) for a, b, _ in got] == [(a, b) for a, b, _ in segs]
+        for (_, _, gt), (_, _, wt) in zip(got, segs):
+            assert [(x[1], x[2]) for x in gt] == [(x[1], x[2]) for x in wt]
+            assert len(gt) == len(wt)
+        assert o["token_count"] == sum(len(s[2]) for s in segs)
+        assert all(s["language"] == "en" for s in o["segments"])
+    eng.close()

@@ -1,0 +1,256 @@
+// Encoder self-attention, generation 2: flash attention on the 5th-generation tensor cores.
+// One CTA = (window, head, 128-query tile); keys/values stream in 128-key tiles:
+//   warp 0 : TMA producer (Q once, then K/V tiles into a 2-stage ring; 128B-swizzled boxes of the
+//            packed [Q | K | V] activation, no separate transposes)
+//   warp 1 : tcgen05.mma issuer - S = Q K^T (128x128x64, both operands K-major) into TMEM, and
+//            O_j = P V_j (128x64x128) with V consumed MN-major straight from its [key][dim] tile
+//   warps 2..5 : softmax. Thread i owns query row i = TMEM lane i: reads S with tcgen05.ld, keeps the
+//            running max / sum, writes P as bf16 into the swizzled smem tile the second MMA reads,
+//            then folds O_j into its f32 register accumulator (acc = acc * alpha + O_j), so TMEM is
+//            never read-modify-written.
+// Two CTAs share an SM (112 KB smem, 256 TMEM columns each): one CTA's softmax overlaps the other's
+// MMAs. Replaces ggml's flash_attn_ext in whisper_encode_internal; generation 1
+// (attn_enc.cu, mma.sync) reached 298 TFLOP/s and was 35 % of the encoder time.
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace sw {
+namespace {
+
+constexpr int TQ = 128, TK = 128, DH = 64;
+constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128 rows][64 bf16] swizzled tile
+constexpr int SM_Q = 0, SM_K = TILE_BYTES, SM_V = 3 * TILE_BYTES, SM_P = 5 * TILE_BYTES;
+constexpr int SM_BARS = 7 * TILE_BYTES;
+constexpr int ATT_SMEM = SM_BARS + 128;
+constexpr int ATT_THREADS = 192;
+constexpr int TMEM_COLS = 256;  // S: columns [0,128), O: [128,192)
+
+// MN-major 128B-swizzled operand (the V tile: rows = keys (K), 64 dims (MN) contiguous per row):
+// canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> SBO = 1024 B between 8-key groups
+__device__ __forceinline__ uint64_t make_umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;   // LBO: unused for a single 64-element MN block
+  d |= static_cast<uint64_t>(64) << 32;  // SBO = 1024 B
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict__ out, int T, int d) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* v_full = bars + 3;    // [2]
+  uint64_t* kv_empty = bars + 5;  // [2]
+  uint64_t* s_full = bars + 7;
+  uint64_t* p_ready = bars + 8;
+  uint64_t* o_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int qt = blockIdx.x, h = blockIdx.y, w = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = qt * TQ;
+  const int n_tiles = (T + TK - 1) / TK;
+  const int row_base = w * T;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) {
+      printf("encoder_attention_tc: shared memory base not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&map_qkv);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, TILE_BYTES);
+      tma_load_2d(smem + SM_Q, &map_qkv, q_full, h * DH, row_base + q0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
+        tma_load_2d(smem + SM_K + s * TILE_BYTES, &map_qkv, &k_full[s], d + h * DH, row_base + j * TK);
+        mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
+        tma_load_2d(smem + SM_V + s * TILE_BYTES, &map_qkv, &v_full[s], 2 * d + h * DH, row_base + j * TK);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);              // S = Q K^T, both K-major
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);  // O = P V, B (V) MN-major
+      const uint32_t sq = smem_u32(smem + SM_Q), sp = smem_u32(smem + SM_P);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const uint32_t sk = smem_u32(smem + SM_K + s * TILE_BYTES), sv = smem_u32(smem + SM_V + s * TILE_BYTES);
+        mbar_wait(&k_full[s], ph);
+        tc_fence_after();
+        {
+          const uint64_t adesc = make_umma_desc_sw128(sq), bdesc = make_umma_desc_sw128(sk);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+        }
+        umma_commit(s_full);
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+        mbar_wait(&v_full[s], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < TK / 16; ++k) {
+          // A = P: two 64-key swizzle atoms of [128 rows][128 B]; B = V: 16 keys = 2 KB per k-step
+          const uint64_t adesc = make_umma_desc_sw128(sp + (k >> 2) * TILE_BYTES) + 2 * (k & 3);
+          const uint64_t bdesc = make_umma_desc_mn_sw128(sv + k * 2048);
+          umma_bf16(tmem + 128, adesc, bdesc, idesc_o, k != 0);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    // ---------------- softmax warps: thread = one query row = one TMEM lane
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const float sc = 0.125f * 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f;
+    float acc[DH];
+#pragma unroll
+    for (int i = 0; i < DH; ++i) acc[i] = 0.f;
+    uint8_t* prow = smem + SM_P + row * 128;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int valid = min(TK, T - j * TK);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem + lane_addr + c * 32, r);
+        tmem_ld_wait();
+        if (c * 32 + 32 <= valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+      }
+      const float mn = fmaxf(m, mx * sc);
+      const float alpha = fast_exp2(m - mn);
+      m = mn;
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem + lane_addr + c * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
+          float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
+          if (c * 32 + 2 * i >= valid) p0 = 0.f;
+          if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
+          lsum += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        // 32 keys = 4 chunks of 16 B; chunk index within the 64-key atom: (c & 1) * 4 + q
+        uint8_t* atom = prow + (c >> 1) * TILE_BYTES;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const int ch = (c & 1) * 4 + qq;
+          *reinterpret_cast<uint4*>(atom + ((ch ^ (row & 7)) << 4)) =
+              make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+        }
+      }
+      l = l * alpha + lsum;
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      // fold O_j into the register accumulator
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem + lane_addr + 128 + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * alpha + __uint_as_float(r[i]);
+      }
+      tc_fence_before();
+    }
+    if (q0 + row < T) {
+      const float inv = 1.0f / l;
+      bf16* op = out + (int64_t)(row_base + q0 + row) * d + h * DH;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 o;
+        o.x = pack_bf16x2(acc[8 * i] * inv, acc[8 * i + 1] * inv);
+        o.y = pack_bf16x2(acc[8 * i + 2] * inv, acc[8 * i + 3] * inv);
+        o.z = pack_bf16x2(acc[8 * i + 4] * inv, acc[8 * i + 5] * inv);
+        o.w = pack_bf16x2(acc[8 * i + 6] * inv, acc[8 * i + 7] * inv);
+        reinterpret_cast<uint4*>(op)[i] = o;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+int encoder_attention_tc(const bf16* qkv, bf16* out, int n_win, int T, int d, int n_head, cudaStream_t stream) {
+  if (n_win <= 0) return 0;
+  SW_CHECK(d == n_head * DH, "encoder_attention: head dim must be 64 (d=%d heads=%d)", d, n_head);
+  static bool attr = false;
+  if (!attr) {
+    SW_CUDA_CHECK(cudaFuncSetAttribute(encoder_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    attr = true;
+  }
+  CUtensorMap map;
+  if (make_tma_map_2d_bf16(&map, qkv, 3 * (int64_t)d, (int64_t)n_win * T, 3 * (int64_t)d, 64, 128)) return -1;
+  dim3 grid((T + TQ - 1) / TQ, n_head, n_win);
+  encoder_attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(map, out, T, d);
+  SW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sw

@@ -114,269 +114,6 @@ self_attention_kernel(const bf16* __restrict__ qkv, const DecRow* __restrict__ r
 }
 
 // ------------------------------------------------------------------------------------------
-// Cross attention, persistent. Work item = (group g = one window and its <= 8 decoder rows,
-// chunk of `spc` 16-key slabs). One CTA per SM walks items blockIdx.x, +gridDim.x, ... so the
-// grid is a whole number of waves whatever the batch size.
-// Warp 8 is the producer: 1-D bulk copies (cp.async.bulk) of 16-key slabs [K row | V row] into a
-// smem ring that keeps running across items; completion on mbarriers. Warps 0..7 consume: warp cw
-// serves decoder cw % cnt and key split cw / cnt, so a slab is read from HBM once however many
-// beams share the window. The next item's query is prefetched while the current one streams.
-// Lane layout: a row of d bf16 is d/8 16-byte chunks; lane owns chunk it*32+lane (8 lanes / head).
-// ------------------------------------------------------------------------------------------
-constexpr int XA_KEYS = 16;
-constexpr int XA_CONSUMERS = 8;
-constexpr int XA_THREADS = (XA_CONSUMERS + 1) * 32;
-constexpr int XA_MAX_CHUNKS = 32;
-
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
-template <int NITER>
-__global__ void __launch_bounds__(XA_THREADS, 1)
-cross_attention_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv,
-                       const int* __restrict__ grp_win, const int* __restrict__ grp_start,
-                       const int* __restrict__ grp_count, int T, int d, int n_head, int spc, int n_stages,
-                       int n_chunks, int n_items, float* __restrict__ ws) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int stage_bytes = XA_KEYS * 2 * d * 2;
-  float* mg = reinterpret_cast<float*>(smem + (size_t)n_stages * stage_bytes);  // [warp][it][lane][10]
-  uint64_t* full = reinterpret_cast<uint64_t*>(mg + XA_CONSUMERS * NITER * 32 * 10);
-  uint64_t* empty = full + n_stages;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunks_per_row = d >> 3;
-  const int row_f = d + 2 * n_head;  // floats per (row, chunk) partial
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < n_stages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], XA_CONSUMERS);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  if (warp == XA_CONSUMERS) {
-    if (lane == 0) {
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int g = item / n_chunks, chunk = item - g * n_chunks;
-        const int win = grp_win[g];
-        const int key_begin = chunk * spc * XA_KEYS;
-        const int key_end = min(T, key_begin + spc * XA_KEYS);
-        const int n_st = (key_end - key_begin + XA_KEYS - 1) / XA_KEYS;
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(kv + ((int64_t)win * T + key_begin) * 2 * d);
-        for (int i = 0; i < n_st; ++i, ++it) {
-          const int s = it % n_stages;
-          const uint32_t ph = (it / n_stages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          const int nk = min(XA_KEYS, key_end - key_begin - i * XA_KEYS);
-          const uint32_t bytes = (uint32_t)nk * 2 * d * 2;
-          mbar_arrive_expect_tx(&full[s], bytes);
-          bulk_g2s(smem + (size_t)s * stage_bytes, src + (size_t)i * stage_bytes, bytes, &full[s]);
-        }
-      }
-    }
-    return;
-  }
-
-  // ---- consumers
-  const float qs = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  uint4 qn[NITER];
-  auto prefetch_q = [&](int item) {
-    const int g = item / n_chunks;
-    const int cnt = grp_count[g], r0 = grp_start[g];
-    const int dd = warp % cnt;
-    const bool act = (warp / cnt) < (XA_CONSUMERS / cnt);
-#pragma unroll
-    for (int it2 = 0; it2 < NITER; ++it2) {
-      const int c = it2 * 32 + lane;
-      qn[it2] = (act && c < chunks_per_row) ? reinterpret_cast<const uint4*>(q + (int64_t)(r0 + dd) * d)[c]
-                                            : make_uint4(0, 0, 0, 0);
-    }
-  };
-  if ((int)blockIdx.x < n_items) prefetch_q(blockIdx.x);
-  int it = 0;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int g = item / n_chunks, chunk = item - g * n_chunks;
-    const int r0 = grp_start[g], cnt = grp_count[g];
-    const int key_begin = chunk * spc * XA_KEYS;
-    const int key_end = min(T, key_begin + spc * XA_KEYS);
-    const int n_st = (key_end - key_begin + XA_KEYS - 1) / XA_KEYS;
-    const int KS = XA_CONSUMERS / cnt;  // key splits per decoder
-    const int dd = warp % cnt, ks = warp / cnt;
-    const bool active = ks < KS;
-    float qf[NITER][8], acc[NITER][8], m[NITER], l[NITER];
-#pragma unroll
-    for (int it2 = 0; it2 < NITER; ++it2) {
-      m[it2] = -INFINITY;
-      l[it2] = 0.f;
-      bf16x8_to_f32(qn[it2], qf[it2]);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        acc[it2][e] = 0.f;
-        qf[it2][e] *= qs;
-      }
-    }
-    if (item + (int)gridDim.x < n_items) prefetch_q(item + gridDim.x);
-    for (int i = 0; i < n_st; ++i, ++it) {
-      const int s = it % n_stages;
-      const uint32_t ph = (it / n_stages) & 1;
-      mbar_wait(&full[s], ph);
-      if (active) {
-        const uint8_t* sb = smem + (size_t)s * stage_bytes;
-        const int nk = min(XA_KEYS, key_end - key_begin - i * XA_KEYS);
-        for (int kk = ks; kk < nk; kk += KS) {
-          const uint4* kr = reinterpret_cast<const uint4*>(sb + (size_t)kk * 4 * d);
-          const uint4* vr = kr + chunks_per_row;
-#pragma unroll
-          for (int it2 = 0; it2 < NITER; ++it2) {
-            const int c = it2 * 32 + lane;
-            const bool ok = c < chunks_per_row;
-            float kf[8], vf[8];
-            const uint4 ku = ok ? kr[c] : make_uint4(0, 0, 0, 0);
-            const uint4 vu = ok ? vr[c] : make_uint4(0, 0, 0, 0);
-            bf16x8_to_f32(ku, kf);
-            bf16x8_to_f32(vu, vf);
-            float sdot = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) sdot += qf[it2][e] * kf[e];
-            sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-            sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-            sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
-            const float mn = fmaxf(m[it2], sdot);
-            const float alpha = fast_exp2(m[it2] - mn);
-            const float p = fast_exp2(sdot - mn);
-            m[it2] = mn;
-            l[it2] = l[it2] * alpha + p;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[it2][e] = acc[it2][e] * alpha + p * vf[e];
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
-    }
-    // ---- merge the key splits of each decoder through the (dedicated) merge area
-    asm volatile("bar.sync 1, %0;" ::"n"(XA_CONSUMERS * 32));
-    if (active && ks > 0) {
-#pragma unroll
-      for (int it2 = 0; it2 < NITER; ++it2) {
-        float* p = mg + ((warp * NITER + it2) * 32 + lane) * 10;
-        p[0] = m[it2];
-        p[1] = l[it2];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) p[2 + e] = acc[it2][e];
-      }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(XA_CONSUMERS * 32));
-    if (active && ks == 0) {
-      for (int k2 = 1; k2 < KS; ++k2) {
-        const int ow = dd + cnt * k2;
-#pragma unroll
-        for (int it2 = 0; it2 < NITER; ++it2) {
-          const float* p = mg + ((ow * NITER + it2) * 32 + lane) * 10;
-          const float m2 = p[0], l2 = p[1];
-          const float mn = fmaxf(m[it2], m2);
-          const float a1 = (m[it2] == -INFINITY) ? 0.f : fast_exp2(m[it2] - mn);
-          const float a2 = (m2 == -INFINITY) ? 0.f : fast_exp2(m2 - mn);
-          l[it2] = l[it2] * a1 + l2 * a2;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[it2][e] = acc[it2][e] * a1 + p[2 + e] * a2;
-          m[it2] = mn;
-        }
-      }
-      float* o = ws + ((int64_t)(r0 + dd) * n_chunks + chunk) * row_f;
-#pragma unroll
-      for (int it2 = 0; it2 < NITER; ++it2) {
-        const int c = it2 * 32 + lane;
-        if (c < chunks_per_row) {
-          reinterpret_cast<float4*>(o + c * 8)[0] = make_float4(acc[it2][0], acc[it2][1], acc[it2][2], acc[it2][3]);
-          reinterpret_cast<float4*>(o + c * 8)[1] = make_float4(acc[it2][4], acc[it2][5], acc[it2][6], acc[it2][7]);
-          if ((lane & 7) == 0) {
-            o[d + (c >> 3)] = m[it2];
-            o[d + n_head + (c >> 3)] = l[it2];
-          }
-        }
-      }
-    }
-  }
-}
-
-__global__ void cross_combine_kernel(const float* __restrict__ ws, int n_chunks, int d, int n_head,
-                                     bf16* __restrict__ out) {
-  const int r = blockIdx.x;
-  const int row_f = d + 2 * n_head;
-  for (int c = threadIdx.x; c < (d >> 3); c += blockDim.x) {
-    const int h = c >> 3;
-    const float* base = ws + (int64_t)r * n_chunks * row_f;
-    float M = -INFINITY;
-    for (int k = 0; k < n_chunks; ++k) M = fmaxf(M, base[(int64_t)k * row_f + d + h]);
-    float L = 0.f, a[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) a[e] = 0.f;
-    for (int k = 0; k < n_chunks; ++k) {
-      const float* p = base + (int64_t)k * row_f;
-      const float mk = p[d + h];
-      const float wgt = (mk == -INFINITY) ? 0.f : fast_exp2(mk - M);
-      L += p[d + n_head + h] * wgt;
-      const float4 x0 = reinterpret_cast<const float4*>(p + c * 8)[0];
-      const float4 x1 = reinterpret_cast<const float4*>(p + c * 8)[1];
-      a[0] += x0.x * wgt; a[1] += x0.y * wgt; a[2] += x0.z * wgt; a[3] += x0.w * wgt;
-      a[4] += x1.x * wgt; a[5] += x1.y * wgt; a[6] += x1.z * wgt; a[7] += x1.w * wgt;
-    }
-    const float inv = 1.0f / L;
-    uint4 o;
-    o.x = pack_bf16x2(a[0] * inv, a[1] * inv);
-    o.y = pack_bf16x2(a[2] * inv, a[3] * inv);
-    o.z = pack_bf16x2(a[4] * inv, a[5] * inv);
-    o.w = pack_bf16x2(a[6] * inv, a[7] * inv);
-    reinterpret_cast<uint4*>(out + (int64_t)r * d)[c] = o;
-  }
-}
-
-int xa_num_sms() {
-  int sms = 148, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sms > 0 ? sms : 148;
-}
-
-// stages per work item: the value that leaves the fewest idle SM-slots in the last wave
-void xa_plan(int n_groups, int T, int d, int* spc_out, int* n_chunks, int* n_stages, int* grid) {
-  const int total_stages = (T + XA_KEYS - 1) / XA_KEYS;
-  const int sms = xa_num_sms();
-  int best_spc = 3;
-  double best_eff = -1.0;
-  for (int spc = 3; spc <= 16; ++spc) {
-    const int nch = (total_stages + spc - 1) / spc;
-    if (nch > XA_MAX_CHUNKS) continue;
-    const int items = n_groups * nch;
-    const int g = items < sms ? items : sms;
-    const int rounds = (items + g - 1) / g;
-    const double eff = (double)n_groups * total_stages / ((double)g * rounds * spc) * (g / (double)sms);
-    if (eff >= best_eff) {
-      best_eff = eff;
-      best_spc = spc;
-    }
-  }
-  *spc_out = best_spc;
-  *n_chunks = (total_stages + best_spc - 1) / best_spc;
-  const int items = n_groups * *n_chunks;
-  *grid = items < sms ? items : sms;
-  const int stage_bytes = XA_KEYS * 2 * d * 2;
-  int ns = (168 * 1024) / stage_bytes;
-  if (ns > 6) ns = 6;
-  if (ns < 2) ns = 2;
-  *n_stages = ns;
-}
-
-// ------------------------------------------------------------------------------------------
 // logits: rules -> log-softmax -> timestamp-vs-text -> argmax or inverse-CDF draws
 // ------------------------------------------------------------------------------------------
 constexpr int LP_THREADS = 1024;
@@ -630,51 +367,6 @@ int self_attention(const bf16* qkv, const DecRow* d_rows, int R, int d, int n_he
   SW_CHECK(d == n_head * 64, "self_attention: head dim must be 64");
   self_attention_kernel<<<dim3(R, n_head), 128, 0, stream>>>(qkv, d_rows, d, pool, d_page_table, layer,
                                                              n_layer, out);
-  SW_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
-size_t cross_attention_ws_floats(int R, int d, int n_head) {
-  return (size_t)R * XA_MAX_CHUNKS * (d + 2 * n_head);
-}
-
-int cross_attention(const bf16* q, const bf16* kv, const int* d_grp_win, const int* d_grp_start,
-                    const int* d_grp_count, int n_groups, int max_count, int R, int T, int d,
-                    int n_head, float* ws, bf16* out, cudaStream_t stream) {
-  if (n_groups <= 0 || R <= 0) return 0;
-  SW_CHECK(d == n_head * 64 && d % 8 == 0, "cross_attention: head dim must be 64");
-  SW_CHECK(max_count >= 1 && max_count <= XA_CONSUMERS, "cross_attention: group of %d rows", max_count);
-  int spc, n_chunks, n_stages, grid;
-  xa_plan(n_groups, T, d, &spc, &n_chunks, &n_stages, &grid);
-  const int niter = (d / 8 + 31) / 32;
-  const int stage_bytes = XA_KEYS * 2 * d * 2;
-  const size_t smem = (size_t)n_stages * stage_bytes + (size_t)XA_CONSUMERS * niter * 32 * 10 * sizeof(float) +
-                      2 * n_stages * sizeof(uint64_t);
-  SW_CHECK(smem <= 227 * 1024, "cross_attention: %zu bytes of shared memory", smem);
-  const int n_items = n_groups * n_chunks;
-#define XA_LAUNCH(NI)                                                                              \
-  do {                                                                                             \
-    static int attr_smem = 0;                                                                      \
-    if (attr_smem < (int)smem) {                                                                   \
-      SW_CUDA_CHECK(cudaFuncSetAttribute(cross_attention_kernel<NI>,                               \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr_smem = (int)smem;                                                                       \
-    }                                                                                              \
-    cross_attention_kernel<NI><<<grid, XA_THREADS, smem, stream>>>(                                \
-        q, kv, d_grp_win, d_grp_start, d_grp_count, T, d, n_head, spc, n_stages, n_chunks,         \
-        n_items, ws);                                                                              \
-  } while (0)
-  switch (niter) {
-    case 1: XA_LAUNCH(1); break;
-    case 2: XA_LAUNCH(2); break;
-    case 3: XA_LAUNCH(3); break;
-    case 4: XA_LAUNCH(4); break;
-    case 5: XA_LAUNCH(5); break;
-    default: set_last_error("cross_attention: unsupported width %d", d); return -1;
-  }
-#undef XA_LAUNCH
-  SW_CUDA_CHECK(cudaGetLastError());
-  cross_combine_kernel<<<R, 160, 0, stream>>>(ws, n_chunks, d, n_head, out);
   SW_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

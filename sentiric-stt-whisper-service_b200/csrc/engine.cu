@@ -3,6 +3,9 @@
 // hand-written kernels in this directory (no cuBLAS/cuDNN/torch).
 #include "engine.h"
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -34,6 +37,10 @@ static int engine_init(Engine* e, const char* path, const sw_ctx_params* p) {
   e->max_beams = (p && p->max_beams > 0) ? p->max_beams : 5;
   SW_CHECK(e->max_beams <= 8, "max_beams %d > 8", e->max_beams);
   e->max_rows = e->max_batch * e->max_beams;
+  {
+    const char* a = getenv("SW_ATTN");  // development switch: SW_ATTN=legacy selects the mma.sync kernel
+    e->legacy_attention = a && strcmp(a, "legacy") == 0;
+  }
   e->model = load_model(path);
   if (!e->model) return -1;
   SW_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -130,7 +137,9 @@ int engine_encode(Engine* e, int n_win, float* enc_out_f32) {
       a.bias = w.bqkv; a.M = (int)M; a.N = 3 * d; a.K = d;
       GEMM(a);
     }
-    if (encoder_attention(e->qkv.p, e->hb.p, n_win, 1500, d, hp.n_audio_head, st)) return -1;
+    if (e->legacy_attention ? encoder_attention(e->qkv.p, e->hb.p, n_win, 1500, d, hp.n_audio_head, st)
+                            : encoder_attention_tc(e->qkv.p, e->hb.p, n_win, 1500, d, hp.n_audio_head, st))
+      return -1;
     {
       GemmArgs a;
       a.A = e->hb.p; a.lda = d; a.B = w.wo; a.ldb = d; a.C = e->x.p; a.ldc = d;
@@ -230,7 +239,7 @@ int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_
     if (skinny_gemm(e->dh.p, d, w.wxq, R, d, d, nullptr, 0, nullptr, 0, part, sp_d, st)) return -1;
     if (reduce_partials(part, sp_d, pstride, R, d, w.bxq, e->dq.p, st)) return -1;
     if (e->kernel_timing) SW_CUDA_CHECK(cudaEventRecord(e->xa_ev[2 * l], st));
-    if (cross_attention(e->dq.p, e->cross_kv.p + l * layer_stride, e->d_grp_win.p,
+    if (cross_attention(e->dq.p, e->cross_kv.p + l * layer_stride, (int64_t)e->max_batch * 1500, e->d_grp_win.p,
                         e->d_grp_start.p, e->d_grp_count.p, n_groups, max_count, R, 1500, d, hp.n_text_head,
                         e->xa_ws.p, e->datt.p, st))
       return -1;

@@ -100,6 +100,7 @@ struct Engine {
 
   StageTimes times;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool legacy_attention = false;
   bool kernel_timing = false;   // bracket each cross_attention launch with events (bench roofline)
   std::vector<cudaEvent_t> xa_ev;
 

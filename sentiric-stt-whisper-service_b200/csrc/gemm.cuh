@@ -43,6 +43,10 @@ int gemm_bf16_tn(const GemmArgs& args, cudaStream_t stream);
 int make_tma_map_2d_bf16(void* map_out, const void* base, int64_t inner, int64_t rows, int64_t ld_elems,
                          int box_inner, int box_rows);
 
+// general 3-D bf16 tensor map (128B swizzle): dims innermost first, strides of dims 1 and 2 in bytes
+int make_tma_map_3d_bf16(void* map_out, const void* base, const int64_t dims[3], const int64_t strides_bytes[2],
+                         const int box[3]);
+
 // FLOPs actually requested (2*M*N*K*batch) - for roofline accounting.
 inline double gemm_flops(const GemmArgs& a) {
   return 2.0 * a.M * (double)a.N * a.K * a.batch;

@@ -388,6 +388,22 @@ int make_tma_map_2d_bf16(void* map_out, const void* base, int64_t inner, int64_t
   return 0;
 }
 
+int make_tma_map_3d_bf16(void* map_out, const void* base, const int64_t dims_in[3], const int64_t strides_bytes[2],
+                         const int box_in[3]) {
+  EncodeTiledFn enc = get_encode_fn();
+  SW_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  SW_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand not 16B aligned");
+  cuuint64_t dims[3] = {(cuuint64_t)dims_in[0], (cuuint64_t)dims_in[1], (cuuint64_t)dims_in[2]};
+  cuuint64_t strides[2] = {(cuuint64_t)strides_bytes[0], (cuuint64_t)strides_bytes[1]};
+  cuuint32_t box[3] = {(cuuint32_t)box_in[0], (cuuint32_t)box_in[1], (cuuint32_t)box_in[2]};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(static_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SW_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+  return 0;
+}
+
 int gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
   SW_CHECK(a.M > 0 && a.N > 0 && a.K > 0 && a.batch > 0, "gemm: empty problem");
   SW_CHECK(a.A && a.B && a.C, "gemm: null operand");

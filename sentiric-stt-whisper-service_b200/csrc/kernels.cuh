@@ -66,6 +66,9 @@ int convert_f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t str
 // non-causal MHA over T keys per (window, head); qkv [n_win*T][3d] bf16 (Q | K | V), out [n_win*T][d].
 int encoder_attention(const bf16* qkv, bf16* out, int n_win, int T, int d, int n_head,
                       cudaStream_t stream);
+// generation 2: tcgen05 / TMEM / TMA flash attention (attn_enc_tc.cu); same contract
+int encoder_attention_tc(const bf16* qkv, bf16* out, int n_win, int T, int d, int n_head,
+                         cudaStream_t stream);
 
 // ------------------------------------------------------------------ decoder (decode.cu)
 constexpr int KV_PAGE = 32;       // tokens per self-KV page
@@ -90,9 +93,10 @@ int self_attention(const bf16* qkv, const DecRow* d_rows, int R, int d, int n_he
 // rows must be grouped by window: window g covers rows [grp_start[g], grp_start[g]+grp_count[g]).
 // workspace: f32, >= n_groups*n_chunks*max_cnt*(d + 2*n_head) ... see cross_attention_ws_floats().
 size_t cross_attention_ws_floats(int R, int d, int n_head);
-int cross_attention(const bf16* q, const bf16* kv, const int* d_grp_win, const int* d_grp_start,
-                    const int* d_grp_count, int n_groups, int max_count, int R, int T, int d,
-                    int n_head, float* ws, bf16* out, cudaStream_t stream);
+// kv_rows: keys the cross-KV buffer of this layer holds (max_batch * T), for the TMA tensor map
+int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d_grp_win,
+                    const int* d_grp_start, const int* d_grp_count, int n_groups, int max_count, int R,
+                    int T, int d, int n_head, float* ws, bf16* out, cudaStream_t stream);
 
 // weight-streaming GEMM for <= 64-row blocks (skinny_gemm.cu): out = X . W^T
 //   split == 1: out bf16 [R][ldo] = act(acc + bias);   split > 1: partial f32 [split][R][N] (raw sums)

@@ -24,7 +24,7 @@ constexpr int SM_Q = 0, SM_K = TILE_BYTES, SM_V = 3 * TILE_BYTES, SM_P = 5 * TIL
 constexpr int SM_BARS = 7 * TILE_BYTES;
 constexpr int ATT_SMEM = SM_BARS + 128;
 constexpr int ATT_THREADS = 192;
-constexpr int TMEM_COLS = 256;  // S: columns [0,128), O: [128,192)
+constexpr int TMEM_COLS = 256;  // S: columns [0,128), O double-buffered: [128,192) and [192,256)
 
 // MN-major 128B-swizzled operand (the V tile: rows = keys (K), 64 dims (MN) contiguous per row):
 // canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> SBO = 1024 B between 8-key groups
@@ -54,8 +54,8 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
   uint64_t* kv_empty = bars + 5;  // [2]
   uint64_t* s_full = bars + 7;
   uint64_t* p_ready = bars + 8;
-  uint64_t* o_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* o_full = bars + 9;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int qt = blockIdx.x, h = blockIdx.y, w = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -77,7 +77,8 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
     }
     mbar_init(s_full, 1);
     mbar_init(p_ready, 4);
-    mbar_init(o_full, 1);
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -109,18 +110,21 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);  // O = P V, B (V) MN-major
       const uint32_t sq = smem_u32(smem + SM_Q), sp = smem_u32(smem + SM_P);
       mbar_wait(q_full, 0);
+      auto issue_s = [&](int j) {  // S_j = Q K_j^T
+        const int s = j & 1;
+        mbar_wait(&k_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t adesc = make_umma_desc_sw128(sq);
+        const uint64_t bdesc = make_umma_desc_sw128(smem_u32(smem + SM_K + s * TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(s_full);
+      };
+      issue_s(0);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        const uint32_t sk = smem_u32(smem + SM_K + s * TILE_BYTES), sv = smem_u32(smem + SM_V + s * TILE_BYTES);
-        mbar_wait(&k_full[s], ph);
-        tc_fence_after();
-        {
-          const uint64_t adesc = make_umma_desc_sw128(sq), bdesc = make_umma_desc_sw128(sk);
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-        }
-        umma_commit(s_full);
+        const uint32_t sv = smem_u32(smem + SM_V + s * TILE_BYTES);
         mbar_wait(p_ready, j & 1);
         tc_fence_after();
         mbar_wait(&v_full[s], ph);
@@ -130,10 +134,13 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
           // A = P: two 64-key swizzle atoms of [128 rows][128 B]; B = V: 16 keys = 2 KB per k-step
           const uint64_t adesc = make_umma_desc_sw128(sp + (k >> 2) * TILE_BYTES) + 2 * (k & 3);
           const uint64_t bdesc = make_umma_desc_mn_sw128(sv + k * 2048);
-          umma_bf16(tmem + 128, adesc, bdesc, idesc_o, k != 0);
+          umma_bf16(tmem + 128 + (j & 1) * 64, adesc, bdesc, idesc_o, k != 0);
         }
-        umma_commit(o_full);
+        umma_commit(&o_full[j & 1]);
         umma_commit(&kv_empty[s]);
+        // S is free again (the softmax warps signalled p_ready after their last read): queue the next
+        // score tile right behind, it runs while they fold O_{j-1} and wait
+        if (j + 1 < n_tiles) issue_s(j + 1);
       }
     }
   } else {
@@ -147,6 +154,20 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
 #pragma unroll
     for (int i = 0; i < DH; ++i) acc[i] = 0.f;
     uint8_t* prow = smem + SM_P + row * 128;
+    float alpha_prev = 1.f;
+    auto fold_o = [&](int j, float a) {  // acc = acc * a + O_j
+      mbar_wait(&o_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem + lane_addr + 128 + (j & 1) * 64 + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * a + __uint_as_float(r[i]);
+      }
+      tc_fence_before();
+    };
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = min(TK, T - j * TK);
       mbar_wait(s_full, j & 1);
@@ -176,14 +197,24 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
         tmem_ld_32x32b_x32(tmem + lane_addr + c * 32, r);
         tmem_ld_wait();
         uint32_t pk[16];
+        if (c * 32 + 32 <= valid) {  // full chunk: no masking
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
-          float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
-          if (c * 32 + 2 * i >= valid) p0 = 0.f;
-          if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
-          lsum += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
+            const float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
+            lsum += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
+            float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
+            if (c * 32 + 2 * i >= valid) p0 = 0.f;
+            if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
+            lsum += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
         }
         // 32 keys = 4 chunks of 16 B; chunk index within the 64-key atom: (c & 1) * 4 + q
         uint8_t* atom = prow + (c >> 1) * TILE_BYTES;
@@ -199,19 +230,11 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
-      // fold O_j into the register accumulator
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem + lane_addr + 128 + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * alpha + __uint_as_float(r[i]);
-      }
-      tc_fence_before();
+      // fold the PREVIOUS tile's O while the tensor core works on this tile's P V and the next Q K^T
+      if (j > 0) fold_o(j - 1, alpha_prev);
+      alpha_prev = alpha;
     }
+    fold_o(n_tiles - 1, alpha_prev);
     if (q0 + row < T) {
       const float inv = 1.0f / l;
       bf16* op = out + (int64_t)(row_base + q0 + row) * d + h * DH;

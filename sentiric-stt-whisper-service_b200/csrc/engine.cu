@@ -6,16 +6,22 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <tuple>
+
 #include "common.cuh"
 #include "gemm.cuh"
 
 namespace sw {
+
+static void engine_free_step_graphs(Engine* e);
 
 Engine::~Engine() {
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   for (auto ev : xa_ev)
     if (ev) cudaEventDestroy(ev);
+  engine_free_step_graphs(this);
   if (stream) cudaStreamDestroy(stream);
   delete model;
 }
@@ -40,6 +46,8 @@ static int engine_init(Engine* e, const char* path, const sw_ctx_params* p) {
   {
     const char* a = getenv("SW_ATTN");  // development switch: SW_ATTN=legacy selects the mma.sync kernel
     e->legacy_attention = a && strcmp(a, "legacy") == 0;
+    const char* g = getenv("SW_GRAPHS");  // development switch: SW_GRAPHS=0 launches the step kernel by kernel
+    e->use_graphs = !(g && strcmp(g, "0") == 0);
   }
   e->model = load_model(path);
   if (!e->model) return -1;
@@ -197,14 +205,15 @@ int engine_copy_pages(Engine* e, const std::vector<int>& pairs) {
   return 0;
 }
 
-int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_logits, int n_lrows,
-                       const LogitCfg& cfg, bool upload_page_table) {
+// Everything one decoder step puts on the stream (uploads, kernels, pick read-back). `launches`
+// counts kernels; `capturing` selects graph-safe event records for the kernel-timing probes.
+static int enqueue_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_logits, int n_lrows,
+                               const LogitCfg& cfg, bool upload_page_table, bool capturing, long* launches) {
   const Model& m = *e->model;
   const HParams& hp = m.hp;
   const int d = hp.n_text_state, L = hp.n_text_layer;
-  SW_CHECK(R > 0 && R <= e->max_rows, "decode step with %d rows (max %d)", R, e->max_rows);
   cudaStream_t st = e->stream;
-  SW_CUDA_CHECK(cudaEventRecord(e->ev0, st));
+  const unsigned ev_flags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
   SW_CUDA_CHECK(cudaMemcpyAsync(e->d_rows.p, e->h_rows.p, R * sizeof(DecRow), cudaMemcpyHostToDevice, st));
   SW_CUDA_CHECK(cudaMemcpyAsync(e->d_tok.p, e->h_tok.p, R * sizeof(int), cudaMemcpyHostToDevice, st));
   SW_CUDA_CHECK(cudaMemcpyAsync(e->d_pos.p, e->h_pos.p, R * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -238,21 +247,21 @@ int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_
     if (layer_norm(e->dx.p, R, d, w.lnx.g, w.lnx.b, e->dh.p, nullptr, part, sp_d, pstride, w.bo, st)) return -1;
     if (skinny_gemm(e->dh.p, d, w.wxq, R, d, d, nullptr, 0, nullptr, 0, part, sp_d, st)) return -1;
     if (reduce_partials(part, sp_d, pstride, R, d, w.bxq, e->dq.p, st)) return -1;
-    if (e->kernel_timing) SW_CUDA_CHECK(cudaEventRecord(e->xa_ev[2 * l], st));
+    if (e->kernel_timing) SW_CUDA_CHECK(cudaEventRecordWithFlags(e->xa_ev[2 * l], st, ev_flags));
     if (cross_attention(e->dq.p, e->cross_kv.p + l * layer_stride, (int64_t)e->max_batch * 1500, e->d_grp_win.p,
                         e->d_grp_start.p, e->d_grp_count.p, n_groups, max_count, R, 1500, d, hp.n_text_head,
                         e->xa_ws.p, e->datt.p, st))
       return -1;
-    if (e->kernel_timing) SW_CUDA_CHECK(cudaEventRecord(e->xa_ev[2 * l + 1], st));
+    if (e->kernel_timing) SW_CUDA_CHECK(cudaEventRecordWithFlags(e->xa_ev[2 * l + 1], st, ev_flags));
     if (skinny_gemm(e->datt.p, d, w.wxo, R, d, d, nullptr, 0, nullptr, 0, part, sp_d, st)) return -1;
     if (layer_norm(e->dx.p, R, d, w.ln2.g, w.ln2.b, e->dh.p, nullptr, part, sp_d, pstride, w.bxo, st)) return -1;
     if (skinny_gemm(e->dh.p, d, w.w1, R, 4 * d, d, w.b1, 1, e->dff.p, 4 * d, nullptr, 1, st)) return -1;
     if (skinny_gemm(e->dff.p, 4 * d, w.w2, R, d, 4 * d, nullptr, 0, nullptr, 0, part, sp_ff, st)) return -1;
     pend_bias = w.b2;
     pend_split = sp_ff;
-    e->times.n_launches += 14;
+    (*launches) += 14;
   }
-  e->times.n_launches += 1;
+  (*launches) += 1;
   if (want_logits || n_lrows > 0) {
     if (layer_norm(e->dx.p, R, d, m.dec_ln.g, m.dec_ln.b, e->dh.p, nullptr, pend_split ? part : nullptr,
                    pend_split, pstride, pend_bias, st))
@@ -260,15 +269,88 @@ int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_
     GemmArgs a;
     a.A = e->dh.p; a.lda = d; a.B = m.tok_emb; a.ldb = d; a.C = e->logits.p; a.ldc = e->logits_ld;
     a.M = R; a.N = hp.n_vocab; a.K = d; a.flags = GEMM_OUT_F32;
-    GEMM(a);
-    e->times.n_launches += 1;
+    if (gemm_bf16_tn(a, e->stream)) return -1;
+    (*launches) += 2;
   }
   if (n_lrows > 0) {
     SW_CUDA_CHECK(cudaMemcpyAsync(e->d_lrows.p, e->h_lrows.p, n_lrows * sizeof(LogitRow), cudaMemcpyHostToDevice, st));
     if (process_logits_pick(e->logits.p, e->logits_ld, e->d_lrows.p, n_lrows, cfg, e->d_picks.p, st)) return -1;
     SW_CUDA_CHECK(cudaMemcpyAsync(e->h_picks.p, e->d_picks.p, (size_t)n_lrows * 8 * sizeof(PickOut),
                                   cudaMemcpyDeviceToHost, st));
-    e->times.n_launches += 1;
+    (*launches) += 1;
+  }
+  return 0;
+}
+
+struct StepKey {
+  int R, G, max_count, want_logits, n_lrows, upload_pt, timing;
+  bool operator<(const StepKey& o) const {
+    return std::tie(R, G, max_count, want_logits, n_lrows, upload_pt, timing) <
+           std::tie(o.R, o.G, o.max_count, o.want_logits, o.n_lrows, o.upload_pt, o.timing);
+  }
+};
+struct StepGraph {
+  cudaGraphExec_t exec = nullptr;
+  long launches = 0;
+};
+struct StepGraphCache {
+  std::map<StepKey, StepGraph> graphs;
+  ~StepGraphCache() {
+    for (auto& kv : graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  }
+};
+
+static void engine_free_step_graphs(Engine* e) {
+  delete static_cast<StepGraphCache*>(e->step_graphs);
+  e->step_graphs = nullptr;
+}
+
+int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_logits, int n_lrows,
+                       const LogitCfg& cfg, bool upload_page_table) {
+  const HParams& hp = e->model->hp;
+  const int d = hp.n_text_state, L = hp.n_text_layer;
+  SW_CHECK(R > 0 && R <= e->max_rows, "decode step with %d rows (max %d)", R, e->max_rows);
+  cudaStream_t st = e->stream;
+  if (!e->use_graphs) {
+    SW_CUDA_CHECK(cudaEventRecord(e->ev0, st));
+    long launches = 0;
+    if (enqueue_decode_step(e, R, n_groups, max_count, want_logits, n_lrows, cfg, upload_page_table, false, &launches))
+      return -1;
+    e->times.n_launches += launches;
+  } else {
+    // The step is a fixed launch sequence for a given shape: capture it once per shape and replay
+    // it (one host call per step instead of ~460, and no inter-kernel launch gaps).
+    if (!e->step_graphs) e->step_graphs = new StepGraphCache();
+    StepGraphCache& cache = *static_cast<StepGraphCache*>(e->step_graphs);
+    const StepKey key{R, n_groups, max_count, want_logits ? 1 : 0, n_lrows, upload_page_table ? 1 : 0,
+                      e->kernel_timing ? 1 : 0};
+    auto it = cache.graphs.find(key);
+    if (it == cache.graphs.end()) {
+      if (cache.graphs.size() > 512) {  // bounded: drop everything and start over
+        for (auto& kv : cache.graphs) cudaGraphExecDestroy(kv.second.exec);
+        cache.graphs.clear();
+      }
+      StepGraph g;
+      SW_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const int rc = enqueue_decode_step(e, R, n_groups, max_count, want_logits, n_lrows, cfg, upload_page_table,
+                                         true, &g.launches);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        if (!rc) set_last_error("decode step graph capture failed: %s", cudaGetErrorString(ce));
+        cudaGetLastError();
+        return -1;
+      }
+      const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      SW_CHECK(ie == cudaSuccess, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+      it = cache.graphs.emplace(key, g).first;
+    }
+    SW_CUDA_CHECK(cudaEventRecord(e->ev0, st));
+    SW_CUDA_CHECK(cudaGraphLaunch(it->second.exec, st));
+    e->times.n_launches += it->second.launches;
   }
   SW_CUDA_CHECK(cudaEventRecord(e->ev1, st));
   SW_CUDA_CHECK(cudaEventSynchronize(e->ev1));

@@ -101,6 +101,8 @@ struct Engine {
   StageTimes times;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool legacy_attention = false;
+  bool use_graphs = true;       // replay each decoder step from a CUDA graph captured per step shape
+  void* step_graphs = nullptr;  // StepGraphCache (engine.cu)
   bool kernel_timing = false;   // bracket each cross_attention launch with events (bench roofline)
   std::vector<cudaEvent_t> xa_ev;
 

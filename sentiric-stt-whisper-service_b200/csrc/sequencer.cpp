@@ -565,7 +565,49 @@ struct Run {
     int max_prompt = 0;
     for (auto& w : wins) max_prompt = std::max(max_prompt, (int)w.prompt.size());
     std::vector<int> prompt_row(nw, -1);
-    for (int pos = 0; pos < max_prompt; ++pos) {
+    int total_prompt_rows = 0;
+    for (auto& w : wins) total_prompt_rows += (int)w.prompt.size();
+    // Common case ([sot, lang, task]): every prompt position of every window in ONE step - the rows
+    // of a window share its cross-KV read (they sit in the M dimension of the cross-attention MMAs)
+    // and self attention is causal over the positions appended in the same step.
+    const bool one_step = total_prompt_rows <= MR && max_prompt <= 8;
+    if (one_step) {
+      int R = 0, G = 0, n_lr = 0, max_cnt = 1;
+      std::vector<std::pair<int, int>> lmap;
+      for (int wi = 0; wi < nw; ++wi) {
+        Window& w = wins[wi];
+        const int s = slot_of(wi, 0), start = R, P = (int)w.prompt.size();
+        for (int pos = 0; pos < P; ++pos) {
+          if (pager.ensure(s, pos)) {
+            set_last_error("self-KV page pool exhausted");
+            return -1;
+          }
+          e->h_rows.p[R] = DecRow{s, pos, wi, 0};
+          e->h_tok.p[R] = w.prompt[pos];
+          e->h_pos.p[R] = pos;
+          ++R;
+        }
+        prompt_row[wi] = R - 1;
+        e->h_grp.p[G] = wi;
+        e->h_grp.p[MR + G] = start;
+        e->h_grp.p[2 * MR + G] = P;
+        max_cnt = std::max(max_cnt, P);
+        ++G;
+      }
+      for (int wi = 0; wi < nw; ++wi)
+        for (int j = 0; j < wins[wi].n_cur && n_lr < MR; ++j) {
+          fill_lrow(e->h_lrows.p[n_lr], wins[wi], j, prompt_row[wi], true);
+          lmap.push_back({wi, j});
+          ++n_lr;
+        }
+      if (engine_decode_step(e, R, G, max_cnt, true, n_lr, cfg, pager.dirty)) return -1;
+      pager.dirty = false;
+      for (auto& w : wins) utts[w.utt].res->n_decode_steps++;
+      for (int k = 0; k < n_lr; ++k) first_picks.push_back({lmap[k].first, lmap[k].second, k});
+      for (int k = 0; k < n_lr; ++k)
+        for (int q = 0; q < 8; ++q) first_store.push_back(e->h_picks.p[k * 8 + q]);
+    }
+    for (int pos = 0; pos < max_prompt && !one_step; ++pos) {
       int R = 0, G = 0, n_lr = 0;
       for (int wi = 0; wi < nw; ++wi) {
         Window& w = wins[wi];

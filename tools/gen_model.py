@@ -35,6 +35,7 @@ SIZES = {
     "small":    (768, 12, 12, 80, 51865),
     "medium":   (1024, 16, 24, 80, 51865),
     "large-v3": (1280, 20, 32, 128, 51866),
+    "large-v3-2l": (1280, 20, 2, 128, 51866),  # large-v3 widths, 2 layers: kernel profiling without the 3 GB file
 }
 
 N_AUDIO_CTX = 1500

@@ -250,9 +250,8 @@ static int enqueue_decode_step(Engine* e, int R, int n_groups, int max_count, bo
     if (e->kernel_timing) SW_CUDA_CHECK(cudaEventRecordWithFlags(e->xa_ev[2 * l], st, ev_flags));
     if (cross_attention(e->dq.p, e->cross_kv.p + l * layer_stride, (int64_t)e->max_batch * 1500, e->d_grp_win.p,
                         e->d_grp_start.p, e->d_grp_count.p, n_groups, max_count, R, 1500, d, hp.n_text_head,
-                        e->xa_ws.p, e->datt.p, st))
+                        e->xa_ws.p, e->datt.p, st, e->kernel_timing ? e->xa_ev[2 * l + 1] : nullptr, ev_flags))
       return -1;
-    if (e->kernel_timing) SW_CUDA_CHECK(cudaEventRecordWithFlags(e->xa_ev[2 * l + 1], st, ev_flags));
     if (skinny_gemm(e->datt.p, d, w.wxo, R, d, d, nullptr, 0, nullptr, 0, part, sp_d, st)) return -1;
     if (layer_norm(e->dx.p, R, d, w.ln2.g, w.ln2.b, e->dh.p, nullptr, part, sp_d, pstride, w.bxo, st)) return -1;
     if (skinny_gemm(e->dh.p, d, w.w1, R, 4 * d, d, w.b1, 1, e->dff.p, 4 * d, nullptr, 1, st)) return -1;

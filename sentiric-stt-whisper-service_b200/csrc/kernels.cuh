@@ -96,7 +96,8 @@ size_t cross_attention_ws_floats(int R, int d, int n_head);
 // kv_rows: keys the cross-KV buffer of this layer holds (max_batch * T), for the TMA tensor map
 int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d_grp_win,
                     const int* d_grp_start, const int* d_grp_count, int n_groups, int max_count, int R,
-                    int T, int d, int n_head, float* ws, bf16* out, cudaStream_t stream);
+                    int T, int d, int n_head, float* ws, bf16* out, cudaStream_t stream,
+                    cudaEvent_t ev_main_done = nullptr, unsigned ev_flags = 0);
 
 // weight-streaming GEMM for <= 64-row blocks (skinny_gemm.cu): out = X . W^T
 //   split == 1: out bf16 [R][ldo] = act(acc + bias);   split > 1: partial f32 [split][R][N] (raw sums)

@@ -218,36 +218,44 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
   }
 }
 
-__global__ void cross_combine_kernel(const float* __restrict__ ws, int n_chunks, int d, int n_head,
-                                     bf16* __restrict__ out) {
+// Merge the per-chunk partials of a row: one warp per (row, group of 4 heads); lane = (head, 8-dim chunk).
+__global__ void __launch_bounds__(32)
+cross_combine_kernel(const float* __restrict__ ws, int n_chunks, int d, int n_head, bf16* __restrict__ out) {
   const int r = blockIdx.x;
+  const int h = blockIdx.y * 4 + (threadIdx.x >> 3);
+  if (h >= n_head) return;
+  const int c = h * 8 + (threadIdx.x & 7);  // 8-float chunk of the row
   const int row_f = d + 2 * n_head;
-  for (int c = threadIdx.x; c < (d >> 3); c += blockDim.x) {
-    const int h = c >> 3;
-    const float* base = ws + (int64_t)r * n_chunks * row_f;
-    float M = -INFINITY;
-    for (int k = 0; k < n_chunks; ++k) M = fmaxf(M, base[(int64_t)k * row_f + d + h]);
-    float L = 0.f, a[8];
+  const float* base = ws + (int64_t)r * n_chunks * row_f;
+  float mk[XA_MAX_CHUNKS];
+  float M = -INFINITY;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) a[e] = 0.f;
-    for (int k = 0; k < n_chunks; ++k) {
-      const float* p = base + (int64_t)k * row_f;
-      const float mk = p[d + h];
-      const float wgt = (mk == -INFINITY) ? 0.f : fast_exp2(mk - M);
-      L += p[d + n_head + h] * wgt;
-      const float4 x0 = reinterpret_cast<const float4*>(p + c * 8)[0];
-      const float4 x1 = reinterpret_cast<const float4*>(p + c * 8)[1];
-      a[0] += x0.x * wgt; a[1] += x0.y * wgt; a[2] += x0.z * wgt; a[3] += x0.w * wgt;
-      a[4] += x1.x * wgt; a[5] += x1.y * wgt; a[6] += x1.z * wgt; a[7] += x1.w * wgt;
+  for (int k = 0; k < XA_MAX_CHUNKS; ++k)
+    if (k < n_chunks) {
+      mk[k] = base[(int64_t)k * row_f + d + h];
+      M = fmaxf(M, mk[k]);
     }
-    const float inv = 1.0f / L;
-    uint4 o;
-    o.x = pack_bf16x2(a[0] * inv, a[1] * inv);
-    o.y = pack_bf16x2(a[2] * inv, a[3] * inv);
-    o.z = pack_bf16x2(a[4] * inv, a[5] * inv);
-    o.w = pack_bf16x2(a[6] * inv, a[7] * inv);
-    reinterpret_cast<uint4*>(out + (int64_t)r * d)[c] = o;
+  float L = 0.f, a[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < n_chunks; ++k) {
+    const float* p = base + (int64_t)k * row_f;
+    const float m1 = p[d + h];
+    const float wgt = (m1 == -INFINITY) ? 0.f : fast_exp2(m1 - M);
+    L += p[d + n_head + h] * wgt;
+    const float4 x0 = reinterpret_cast<const float4*>(p + c * 8)[0];
+    const float4 x1 = reinterpret_cast<const float4*>(p + c * 8)[1];
+    a[0] += x0.x * wgt; a[1] += x0.y * wgt; a[2] += x0.z * wgt; a[3] += x0.w * wgt;
+    a[4] += x1.x * wgt; a[5] += x1.y * wgt; a[6] += x1.z * wgt; a[7] += x1.w * wgt;
   }
+  const float inv = 1.0f / L;
+  uint4 o;
+  o.x = pack_bf16x2(a[0] * inv, a[1] * inv);
+  o.y = pack_bf16x2(a[2] * inv, a[3] * inv);
+  o.z = pack_bf16x2(a[4] * inv, a[5] * inv);
+  o.w = pack_bf16x2(a[6] * inv, a[7] * inv);
+  reinterpret_cast<uint4*>(out + (int64_t)r * d)[c] = o;
 }
 
 int xa_num_sms() {
@@ -294,7 +302,8 @@ size_t cross_attention_ws_floats(int R, int d, int n_head) {
 
 int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d_grp_win,
                     const int* d_grp_start, const int* d_grp_count, int n_groups, int max_count, int R,
-                    int T, int d, int n_head, float* ws, bf16* out, cudaStream_t stream) {
+                    int T, int d, int n_head, float* ws, bf16* out, cudaStream_t stream,
+                    cudaEvent_t ev_main_done, unsigned ev_flags) {
   if (n_groups <= 0 || R <= 0) return 0;
   SW_CHECK(d == n_head * 64, "cross_attention: head dim must be 64");
   SW_CHECK(max_count >= 1 && max_count <= 8, "cross_attention: group of %d rows", max_count);
@@ -337,7 +346,8 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
   }
 #undef XA_LAUNCH
   SW_CUDA_CHECK(cudaGetLastError());
-  cross_combine_kernel<<<R, 160, 0, stream>>>(ws, n_chunks, d, n_head, out);
+  if (ev_main_done) SW_CUDA_CHECK(cudaEventRecordWithFlags(ev_main_done, stream, ev_flags));
+  cross_combine_kernel<<<dim3(R, (n_head + 3) / 4), 32, 0, stream>>>(ws, n_chunks, d, n_head, out);
   SW_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

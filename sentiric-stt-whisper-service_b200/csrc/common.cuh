@@ -65,6 +65,41 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ----------------------------------------------------------------------------
+// Programmatic dependent launch (PDL). The ~450 kernels of a decoder step form one dependency
+// chain of launches that each take a few microseconds; with PDL the next kernel's CTAs become
+// resident (and run their prologue: barrier init, descriptor prefetch, weight prefetch) while the
+// previous kernel is still executing, and block in pdl_wait() until its results are visible.
+//   * pdl_launch_dependents(): first statement of every chained kernel.
+//   * pdl_wait(): before the first global read of a predecessor's output AND before the first
+//     global write (the predecessor may still be reading what we are about to overwrite).
+// Both are no-ops for a kernel launched without the attribute. Host side: launch_pdl().
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+bool pdl_enabled();  // engine.cu: on unless SW_PDL=0
+
+// Launch `kernel` with the programmatic-stream-serialization attribute (plain launch if PDL is off).
+// Only kernels that call pdl_wait() may be launched through this.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ----------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

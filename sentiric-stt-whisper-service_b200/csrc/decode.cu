@@ -21,27 +21,7 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
   f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 
-__device__ __forceinline__ const bf16* page_ptr(const bf16* pool, const int* page_table, int slot,
-                                                int pos, int layer, int n_layer, int kv, int d) {
-  const int page = page_table[slot * KV_MAX_PAGES + pos / KV_PAGE];
-  return pool + ((((int64_t)page * n_layer + layer) * 2 + kv) * KV_PAGE + (pos % KV_PAGE)) * d;
-}
-
 // ------------------------------------------------------------------------------------------
-__global__ void kv_append_kernel(const bf16* __restrict__ qkv, const DecRow* __restrict__ rows, int d,
-                                 bf16* __restrict__ pool, const int* __restrict__ page_table, int layer,
-                                 int n_layer) {
-  const DecRow r = rows[blockIdx.x];
-  const uint4* src = reinterpret_cast<const uint4*>(qkv + (int64_t)blockIdx.x * 3 * d + d);
-  uint4* dk = reinterpret_cast<uint4*>(const_cast<bf16*>(page_ptr(pool, page_table, r.slot, r.pos, layer, n_layer, 0, d)));
-  uint4* dv = reinterpret_cast<uint4*>(const_cast<bf16*>(page_ptr(pool, page_table, r.slot, r.pos, layer, n_layer, 1, d)));
-  const int nv = d / 8;
-  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-    dk[i] = src[i];
-    dv[i] = src[nv + i];
-  }
-}
-
 __global__ void kv_copy_pages_kernel(bf16* __restrict__ pool, const int* __restrict__ pairs, int64_t page_elems) {
   const int src = pairs[2 * blockIdx.y], dst = pairs[2 * blockIdx.y + 1];
   const uint4* s = reinterpret_cast<const uint4*>(pool + (int64_t)src * page_elems);
@@ -51,23 +31,74 @@ __global__ void kv_copy_pages_kernel(bf16* __restrict__ pool, const int* __restr
     d[i] = s[i];
 }
 
-// one CTA (128 threads) per (row, head); n_kv = pos + 1 <= 448
+// one CTA (128 threads) per (row, head); n_kv = pos + 1 <= 448. The CTA also appends the row's own
+// K/V head slice to the paged cache (no separate append launch); keys of positions >= pos0 are
+// produced by rows of this same step and are read from the qkv buffer, not from the cache.
+// Built for latency, not throughput (the whole launch moves a few MB): the row descriptor carries
+// its page list, so the dependent chain is descriptor -> K and V loads (issued together, V kept in
+// registers while the softmax statistics are reduced) -> store. Generation 1 walked the keys of the
+// P.V product one dependent load at a time and cost 13 us per layer inside the step graph.
+__device__ __forceinline__ const bf16* sa_kv_ptr(const bf16* pool, const DecRow& row, const bf16* own, int k, int kv,
+                                                 int layer, int n_layer, int d, int h) {
+  if (k >= row.pos0) return own - (int64_t)(row.pos - k) * 3 * d + (1 + kv) * d;  // produced in this step
+  const int page = row.pages[k / KV_PAGE];
+  return pool + ((((int64_t)page * n_layer + layer) * 2 + kv) * KV_PAGE + (k % KV_PAGE)) * d + h * 64;
+}
+
 __global__ void __launch_bounds__(128)
 self_attention_kernel(const bf16* __restrict__ qkv, const DecRow* __restrict__ rows, int d,
-                      const bf16* __restrict__ pool, const int* __restrict__ page_table, int layer,
-                      int n_layer, bf16* __restrict__ out) {
+                      bf16* __restrict__ pool, int layer, int n_layer, bf16* __restrict__ out) {
+  __shared__ DecRow row;
   __shared__ float qs[64];
   __shared__ float sc[448];
   __shared__ float red[4];
-  __shared__ float part[4][64];
+  __shared__ float part[16][65];
   const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
-  const DecRow row = rows[r];
-  const int n_kv = row.pos + 1;
-  if (tid < 64) qs[tid] = __bfloat162float(qkv[(int64_t)r * 3 * d + h * 64 + tid]) * 0.125f;
+  pdl_launch_dependents();
+  pdl_wait();
+  const bf16* own = qkv + (int64_t)r * 3 * d + h * 64;  // q | k (+d) | v (+2d) of this row and head
+  constexpr int ROW_INTS = sizeof(DecRow) / 4;
+  if (tid < ROW_INTS) reinterpret_cast<int*>(&row)[tid] = reinterpret_cast<const int*>(rows + r)[tid];
+  uint4 mine = make_uint4(0, 0, 0, 0);
+  if (tid >= 32 && tid < 48) mine = reinterpret_cast<const uint4*>(own + (1 + ((tid - 32) >> 3)) * d)[tid & 7];
+  if (tid >= 64) qs[tid - 64] = __bfloat162float(own[tid - 64]) * 0.125f;
   __syncthreads();
+  const int n_kv = row.pos + 1;
+  if (tid >= 32 && tid < 48) {  // append: 2 x 128 bytes
+    const int kv = (tid - 32) >> 3;
+    const int page = row.pages[row.pos / KV_PAGE];
+    bf16* dst = pool + ((((int64_t)page * n_layer + layer) * 2 + kv) * KV_PAGE + (row.pos % KV_PAGE)) * d + h * 64;
+    reinterpret_cast<uint4*>(dst)[tid & 7] = mine;
+  }
+  // ---- issue the K loads (thread = key) and the first V loads (thread = (key group, 8-dim chunk)) together
+  const int kg = tid >> 3, vc = tid & 7;
+  uint4 kreg[8], vreg[4];
+  if (tid < n_kv) {
+    const uint4* kp = reinterpret_cast<const uint4*>(sa_kv_ptr(pool, row, own, tid, 0, layer, n_layer, d, h));
+#pragma unroll
+    for (int c = 0; c < 8; ++c) kreg[c] = kp[c];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = kg + 16 * j;
+    vreg[j] = make_uint4(0, 0, 0, 0);
+    if (k < n_kv) vreg[j] = reinterpret_cast<const uint4*>(sa_kv_ptr(pool, row, own, k, 1, layer, n_layer, d, h))[vc];
+  }
   float lmax = -INFINITY;
-  for (int k = tid; k < n_kv; k += 128) {
-    const uint4* kp = reinterpret_cast<const uint4*>(page_ptr(pool, page_table, row.slot, k, layer, n_layer, 0, d) + h * 64);
+  if (tid < n_kv) {
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float f[8];
+      bf16x8_to_f32(kreg[c], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc += qs[c * 8 + e] * f[e];
+    }
+    sc[tid] = acc;
+    lmax = acc;
+  }
+  for (int k = tid + 128; k < n_kv; k += 128) {  // long contexts
+    const uint4* kp = reinterpret_cast<const uint4*>(sa_kv_ptr(pool, row, own, k, 0, layer, n_layer, d, h));
     float acc = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -94,22 +125,49 @@ self_attention_kernel(const bf16* __restrict__ qkv, const DecRow* __restrict__ r
   if ((tid & 31) == 0) red[tid >> 5] = lsum;
   __syncthreads();
   const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
-  // P.V: warp w takes keys w, w+4, ...; lane owns dims 2*lane, 2*lane+1
-  const int w = tid >> 5, lane = tid & 31;
-  float a0 = 0.f, a1 = 0.f;
-  for (int k = w; k < n_kv; k += 4) {
-    const bf16* vp = page_ptr(pool, page_table, row.slot, k, layer, n_layer, 1, d) + h * 64;
-    const uint32_t u = reinterpret_cast<const uint32_t*>(vp)[lane];
-    const float p = sc[k];
-    a0 += p * __uint_as_float(u << 16);
-    a1 += p * __uint_as_float(u & 0xffff0000u);
+  // ---- P.V: thread (kg, vc) accumulates keys kg, kg+16, ... for dims vc*8..vc*8+7
+  float a[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = kg + 16 * j;
+    if (k < n_kv) {
+      const float p = sc[k];
+      float f[8];
+      bf16x8_to_f32(vreg[j], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] += p * f[e];
+    }
   }
-  part[w][2 * lane] = a0;
-  part[w][2 * lane + 1] = a1;
+  for (int k0 = 64; k0 < n_kv; k0 += 64) {
+    uint4 v4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + kg + 16 * j;
+      v4[j] = make_uint4(0, 0, 0, 0);
+      if (k < n_kv) v4[j] = reinterpret_cast<const uint4*>(sa_kv_ptr(pool, row, own, k, 1, layer, n_layer, d, h))[vc];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + kg + 16 * j;
+      if (k < n_kv) {
+        const float p = sc[k];
+        float f[8];
+        bf16x8_to_f32(v4[j], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] += p * f[e];
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[kg][vc * 8 + e] = a[e];
   __syncthreads();
   if (tid < 64) {
-    const float v = (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]) * inv;
-    out[(int64_t)r * d + h * 64 + tid] = __float2bfloat16_rn(v);
+    float v = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) v += part[g][tid];
+    out[(int64_t)r * d + h * 64 + tid] = __float2bfloat16_rn(v * inv);
   }
 }
 
@@ -181,6 +239,8 @@ process_logits_kernel(const float* __restrict__ logits, int64_t ld, const LogitR
   __shared__ int redi[LP_THREADS / 32];
   __shared__ double redd[LP_THREADS / 32];
   __shared__ double seg_prefix[LP_THREADS];
+  pdl_launch_dependents();
+  pdl_wait();
   const LogitRow row = rows[blockIdx.x];
   const float* src = logits + (int64_t)row.logits_row * ld;
   const int n = cfg.n_vocab, beg = cfg.token_beg, tid = threadIdx.x;
@@ -346,14 +406,6 @@ process_logits_kernel(const float* __restrict__ logits, int64_t ld, const LogitR
 
 }  // namespace
 
-int kv_append(const bf16* qkv, const DecRow* d_rows, int R, int d, bf16* pool, const int* d_page_table,
-              int layer, int n_layer, cudaStream_t stream) {
-  if (R <= 0) return 0;
-  kv_append_kernel<<<R, 128, 0, stream>>>(qkv, d_rows, d, pool, d_page_table, layer, n_layer);
-  SW_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
 int kv_copy_pages(bf16* pool, const int* d_pairs, int n, int64_t page_elems, cudaStream_t stream) {
   if (n <= 0) return 0;
   kv_copy_pages_kernel<<<dim3(32, n), 256, 0, stream>>>(pool, d_pairs, page_elems);
@@ -361,13 +413,12 @@ int kv_copy_pages(bf16* pool, const int* d_pairs, int n, int64_t page_elems, cud
   return 0;
 }
 
-int self_attention(const bf16* qkv, const DecRow* d_rows, int R, int d, int n_head, const bf16* pool,
-                   const int* d_page_table, int layer, int n_layer, bf16* out, cudaStream_t stream) {
+int self_attention(const bf16* qkv, const DecRow* d_rows, int R, int d, int n_head, bf16* pool,
+                   int layer, int n_layer, bf16* out, cudaStream_t stream) {
   if (R <= 0) return 0;
   SW_CHECK(d == n_head * 64, "self_attention: head dim must be 64");
-  self_attention_kernel<<<dim3(R, n_head), 128, 0, stream>>>(qkv, d_rows, d, pool, d_page_table, layer,
-                                                             n_layer, out);
-  SW_CUDA_CHECK(cudaGetLastError());
+  SW_CUDA_CHECK(launch_pdl(self_attention_kernel, dim3(R, n_head), dim3(128), 0, stream, qkv, d_rows, d, pool,
+                           layer, n_layer, out));
   return 0;
 }
 

@@ -86,17 +86,31 @@ layer_norm_row_kernel(float* __restrict__ x, int d, const float* __restrict__ g,
   const int row = blockIdx.x, t = threadIdx.x;
   const int nch = d >> 3;
   const bool act = t < nch;
+  pdl_launch_dependents();
+  // model constants first: they do not depend on the previous kernel of the step
+  float gg[8], bb[8], ab[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) gg[i] = bb[i] = ab[i] = 0.f;
+  if (act) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + t * 8)), g1 = __ldg(reinterpret_cast<const float4*>(g + t * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + t * 8)), b1 = __ldg(reinterpret_cast<const float4*>(b + t * 8) + 1);
+    gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+    bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+    if (partial && add_bias) {
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(add_bias + t * 8));
+      const float4 c1 = __ldg(reinterpret_cast<const float4*>(add_bias + t * 8) + 1);
+      ab[0] = c0.x; ab[1] = c0.y; ab[2] = c0.z; ab[3] = c0.w; ab[4] = c1.x; ab[5] = c1.y; ab[6] = c1.z; ab[7] = c1.w;
+    }
+  }
+  pdl_wait();
   float v[8];
   float* xr = x + (int64_t)row * d + t * 8;
   if (act) {
     const float4 a0 = reinterpret_cast<const float4*>(xr)[0], a1 = reinterpret_cast<const float4*>(xr)[1];
     v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
     if (partial) {
-      if (add_bias) {
-        const float4 c0 = __ldg(reinterpret_cast<const float4*>(add_bias + t * 8));
-        const float4 c1 = __ldg(reinterpret_cast<const float4*>(add_bias + t * 8) + 1);
-        v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w; v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
-      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += ab[i];
       float4 p0[8], p1[8];
 #pragma unroll
       for (int s = 0; s < 8; ++s)
@@ -146,10 +160,6 @@ layer_norm_row_kernel(float* __restrict__ x, int d, const float* __restrict__ g,
   for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tsq += red[i];
   const float scale = rsqrtf(tsq / (float)d + 1e-5f);
   if (!act) return;
-  const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + t * 8)), g1 = __ldg(reinterpret_cast<const float4*>(g + t * 8) + 1);
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + t * 8)), b1 = __ldg(reinterpret_cast<const float4*>(b + t * 8) + 1);
-  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   float o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = (v[i] - mean) * scale * gg[i] + bb[i];
@@ -170,6 +180,8 @@ __global__ void __launch_bounds__(192)
 reduce_partials_kernel(const float* __restrict__ partial, int n_split, int64_t split_stride, int d,
                        const float* __restrict__ bias, bf16* __restrict__ out) {
   const int row = blockIdx.x, t = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (t >= (d >> 3)) return;
   float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (bias) {
@@ -200,6 +212,8 @@ __global__ void embed_tokens_kernel(const bf16* __restrict__ tok_emb, const floa
                                     const int* __restrict__ tok, const int* __restrict__ pos, int d,
                                     float* __restrict__ x) {
   const int r = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();  // x may still be read by the previous step's last kernels
   const bf16* e = tok_emb + (int64_t)tok[r] * d;
   const float* p = pos_emb + (int64_t)pos[r] * d;
   for (int i = threadIdx.x; i < d; i += blockDim.x) x[(int64_t)r * d + i] = __bfloat162float(e[i]) + p[i];
@@ -223,9 +237,8 @@ int layer_norm(float* x, int rows, int d, const float* g, const float* b, bf16* 
   SW_CHECK(d % 128 == 0 && d <= 128 * LN_MAX_V4, "layer_norm: unsupported width %d", d);
   if (rows <= 2048) {  // decoder step: spread the few rows over as many SMs
     const int threads = ((d >> 3) + 31) / 32 * 32;
-    layer_norm_row_kernel<<<rows, threads, 0, stream>>>(x, d, g, b, out_bf16, out_f32, partial, n_split,
-                                                        split_stride, add_bias);
-    SW_CUDA_CHECK(cudaGetLastError());
+    SW_CUDA_CHECK(launch_pdl(layer_norm_row_kernel, dim3(rows), dim3(threads), 0, stream, x, d, g, b, out_bf16,
+                             out_f32, partial, n_split, split_stride, add_bias));
     return 0;
   }
   layer_norm_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(x, rows, d, g, b, out_bf16, out_f32, partial,
@@ -238,8 +251,8 @@ int reduce_partials(const float* partial, int n_split, int64_t split_stride, int
                     const float* bias, bf16* out, cudaStream_t stream) {
   if (rows <= 0) return 0;
   SW_CHECK(d % 8 == 0 && d <= 1536, "reduce_partials: unsupported width %d", d);
-  reduce_partials_kernel<<<rows, ((d >> 3) + 31) / 32 * 32, 0, stream>>>(partial, n_split, split_stride, d, bias, out);
-  SW_CUDA_CHECK(cudaGetLastError());
+  SW_CUDA_CHECK(launch_pdl(reduce_partials_kernel, dim3(rows), dim3(((d >> 3) + 31) / 32 * 32), 0, stream, partial,
+                           n_split, split_stride, d, bias, out));
   return 0;
 }
 

@@ -16,6 +16,17 @@ namespace sw {
 
 static void engine_free_step_graphs(Engine* e);
 
+// Programmatic dependent launch of the step kernels is OFF unless SW_PDL=1: measured inside the step
+// graph it costs 7 % (154.7 vs 144.1 us per layer, profiles/r1_step_kernel_costs_pdl_*.log) - early-resident
+// dependents take SM slots from the kernel they wait for, and a graph edge is already only ~1.5 us.
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* p = getenv("SW_PDL");
+    return p && strcmp(p, "1") == 0;
+  }();
+  return on;
+}
+
 Engine::~Engine() {
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -100,6 +111,8 @@ Engine* engine_create(const char* model_path, const sw_ctx_params* params) {
   }
   return e;
 }
+
+constexpr int XA_TIMED_EVERY = 8;
 
 #define GEMM(args)                                   \
   do {                                               \
@@ -220,9 +233,8 @@ static int enqueue_decode_step(Engine* e, int R, int n_groups, int max_count, bo
   SW_CUDA_CHECK(cudaMemcpyAsync(e->d_grp_win.p, e->h_grp.p, n_groups * sizeof(int), cudaMemcpyHostToDevice, st));
   SW_CUDA_CHECK(cudaMemcpyAsync(e->d_grp_start.p, e->h_grp.p + e->max_rows, n_groups * sizeof(int), cudaMemcpyHostToDevice, st));
   SW_CUDA_CHECK(cudaMemcpyAsync(e->d_grp_count.p, e->h_grp.p + 2 * e->max_rows, n_groups * sizeof(int), cudaMemcpyHostToDevice, st));
-  if (upload_page_table)
-    SW_CUDA_CHECK(cudaMemcpyAsync(e->d_page_table.p, e->h_page_table.p,
-                                  (size_t)e->max_rows * KV_MAX_PAGES * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (n_lrows > 0)  // up front, so that nothing but kernels sits between the step's kernels (PDL chain)
+    SW_CUDA_CHECK(cudaMemcpyAsync(e->d_lrows.p, e->h_lrows.p, n_lrows * sizeof(LogitRow), cudaMemcpyHostToDevice, st));
   if (embed_tokens(m.tok_emb, m.dec_pos, e->d_tok.p, e->d_pos.p, R, d, e->dx.p, st)) return -1;
   const int64_t layer_stride = (int64_t)e->max_batch * 1500 * 2 * d;
   // Weight-streaming GEMMs (skinny_gemm.cu). Projections that feed the residual stream or the
@@ -233,33 +245,47 @@ static int enqueue_decode_step(Engine* e, int R, int n_groups, int max_count, bo
   float* part = e->dpart.p;
   const float* pend_bias = nullptr;  // bias of the FC2 partials still to be folded into x
   int pend_split = 0;
+  // development switch: SW_SKIP=<bitmask> leaves kernels out of the step (results are garbage) so that
+  // the in-graph cost of each one can be read off as a time difference (tools/dev_step_time.py)
+  static const int skip = getenv("SW_SKIP") ? atoi(getenv("SW_SKIP")) : 0;
+#define STEP_K(bit, call)                    \
+  do {                                       \
+    if (!(skip & (bit))) {                   \
+      if (call) return -1;                   \
+      ++*launches;                           \
+    }                                        \
+  } while (0)
   for (int l = 0; l < L; ++l) {
     const DecLayerW& w = m.dec[l];
-    if (layer_norm(e->dx.p, R, d, w.ln1.g, w.ln1.b, e->dh.p, nullptr, pend_split ? part : nullptr, pend_split,
-                   pstride, pend_bias, st))
-      return -1;
-    if (skinny_gemm(e->dh.p, d, w.wqkv, R, 3 * d, d, w.bqkv, 0, e->dqkv.p, 3 * d, nullptr, 1, st)) return -1;
-    if (kv_append(e->dqkv.p, e->d_rows.p, R, d, e->kv_pool.p, e->d_page_table.p, l, L, st)) return -1;
-    if (self_attention(e->dqkv.p, e->d_rows.p, R, d, hp.n_text_head, e->kv_pool.p, e->d_page_table.p, l, L,
-                       e->datt.p, st))
-      return -1;
-    if (skinny_gemm(e->datt.p, d, w.wo, R, d, d, nullptr, 0, nullptr, 0, part, sp_d, st)) return -1;
-    if (layer_norm(e->dx.p, R, d, w.lnx.g, w.lnx.b, e->dh.p, nullptr, part, sp_d, pstride, w.bo, st)) return -1;
-    if (skinny_gemm(e->dh.p, d, w.wxq, R, d, d, nullptr, 0, nullptr, 0, part, sp_d, st)) return -1;
-    if (reduce_partials(part, sp_d, pstride, R, d, w.bxq, e->dq.p, st)) return -1;
-    if (e->kernel_timing) SW_CUDA_CHECK(cudaEventRecordWithFlags(e->xa_ev[2 * l], st, ev_flags));
-    if (cross_attention(e->dq.p, e->cross_kv.p + l * layer_stride, (int64_t)e->max_batch * 1500, e->d_grp_win.p,
-                        e->d_grp_start.p, e->d_grp_count.p, n_groups, max_count, R, 1500, d, hp.n_text_head,
-                        e->xa_ws.p, e->datt.p, st, e->kernel_timing ? e->xa_ev[2 * l + 1] : nullptr, ev_flags))
-      return -1;
-    if (skinny_gemm(e->datt.p, d, w.wxo, R, d, d, nullptr, 0, nullptr, 0, part, sp_d, st)) return -1;
-    if (layer_norm(e->dx.p, R, d, w.ln2.g, w.ln2.b, e->dh.p, nullptr, part, sp_d, pstride, w.bxo, st)) return -1;
-    if (skinny_gemm(e->dh.p, d, w.w1, R, 4 * d, d, w.b1, 1, e->dff.p, 4 * d, nullptr, 1, st)) return -1;
-    if (skinny_gemm(e->dff.p, 4 * d, w.w2, R, d, 4 * d, nullptr, 0, nullptr, 0, part, sp_ff, st)) return -1;
+    STEP_K(1, layer_norm(e->dx.p, R, d, w.ln1.g, w.ln1.b, e->dh.p, nullptr, pend_split ? part : nullptr, pend_split,
+                         pstride, pend_bias, st));
+    STEP_K(2, skinny_gemm(e->dh.p, d, w.wqkv, R, 3 * d, d, w.bqkv, 0, e->dqkv.p, 3 * d, nullptr, 1, st));
+    STEP_K(4, self_attention(e->dqkv.p, e->d_rows.p, R, d, hp.n_text_head, e->kv_pool.p, l, L, e->datt.p, st));
+    STEP_K(8, skinny_gemm(e->datt.p, d, w.wo, R, d, d, nullptr, 0, nullptr, 0, part, sp_d, st));
+    STEP_K(1, layer_norm(e->dx.p, R, d, w.lnx.g, w.lnx.b, e->dh.p, nullptr, part, sp_d, pstride, w.bo, st));
+    STEP_K(16, skinny_gemm(e->dh.p, d, w.wxq, R, d, d, nullptr, 0, nullptr, 0, part, sp_d, st));
+    STEP_K(32, reduce_partials(part, sp_d, pstride, R, d, w.bxq, e->dq.p, st));
+    // kernel-timing probes bracket the cross attention of every XA_TIMED_EVERY-th layer only: an event
+    // node between two kernels turns their programmatic edge into a full dependency
+    const bool timed = e->kernel_timing && l % XA_TIMED_EVERY == 0;
+    if (timed) SW_CUDA_CHECK(cudaEventRecordWithFlags(e->xa_ev[2 * l], st, ev_flags));
+    if (!(skip & 64)) {
+      if (cross_attention(e->dq.p, e->cross_kv.p + l * layer_stride, (int64_t)e->max_batch * 1500, e->d_grp_win.p,
+                          e->d_grp_start.p, e->d_grp_count.p, n_groups, max_count, R, 1500, d, hp.n_text_head,
+                          e->xa_ws.p, e->datt.p, st, timed ? e->xa_ev[2 * l + 1] : nullptr, ev_flags))
+        return -1;
+      *launches += 2;
+    } else if (timed) {
+      SW_CUDA_CHECK(cudaEventRecordWithFlags(e->xa_ev[2 * l + 1], st, ev_flags));
+    }
+    STEP_K(256, skinny_gemm(e->datt.p, d, w.wxo, R, d, d, nullptr, 0, nullptr, 0, part, sp_d, st));
+    STEP_K(1, layer_norm(e->dx.p, R, d, w.ln2.g, w.ln2.b, e->dh.p, nullptr, part, sp_d, pstride, w.bxo, st));
+    STEP_K(512, skinny_gemm(e->dh.p, d, w.w1, R, 4 * d, d, w.b1, 1, e->dff.p, 4 * d, nullptr, 1, st));
+    STEP_K(1024, skinny_gemm(e->dff.p, 4 * d, w.w2, R, d, 4 * d, nullptr, 0, nullptr, 0, part, sp_ff, st));
     pend_bias = w.b2;
     pend_split = sp_ff;
-    (*launches) += 14;
   }
+#undef STEP_K
   (*launches) += 1;
   if (want_logits || n_lrows > 0) {
     if (layer_norm(e->dx.p, R, d, m.dec_ln.g, m.dec_ln.b, e->dh.p, nullptr, pend_split ? part : nullptr,
@@ -272,7 +298,6 @@ static int enqueue_decode_step(Engine* e, int R, int n_groups, int max_count, bo
     (*launches) += 2;
   }
   if (n_lrows > 0) {
-    SW_CUDA_CHECK(cudaMemcpyAsync(e->d_lrows.p, e->h_lrows.p, n_lrows * sizeof(LogitRow), cudaMemcpyHostToDevice, st));
     if (process_logits_pick(e->logits.p, e->logits_ld, e->d_lrows.p, n_lrows, cfg, e->d_picks.p, st)) return -1;
     SW_CUDA_CHECK(cudaMemcpyAsync(e->h_picks.p, e->d_picks.p, (size_t)n_lrows * 8 * sizeof(PickOut),
                                   cudaMemcpyDeviceToHost, st));
@@ -311,6 +336,9 @@ int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_
   const int d = hp.n_text_state, L = hp.n_text_layer;
   SW_CHECK(R > 0 && R <= e->max_rows, "decode step with %d rows (max %d)", R, e->max_rows);
   cudaStream_t st = e->stream;
+  for (int r = 0; r < R; ++r)  // each row carries its slot's page list (the host table is the pager's)
+    memcpy(e->h_rows.p[r].pages, e->h_page_table.p + (size_t)e->h_rows.p[r].slot * KV_MAX_PAGES,
+           KV_MAX_PAGES * sizeof(int));
   if (!e->use_graphs) {
     SW_CUDA_CHECK(cudaEventRecord(e->ev0, st));
     long launches = 0;
@@ -322,8 +350,7 @@ int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_
     // it (one host call per step instead of ~460, and no inter-kernel launch gaps).
     if (!e->step_graphs) e->step_graphs = new StepGraphCache();
     StepGraphCache& cache = *static_cast<StepGraphCache*>(e->step_graphs);
-    const StepKey key{R, n_groups, max_count, want_logits ? 1 : 0, n_lrows, upload_page_table ? 1 : 0,
-                      e->kernel_timing ? 1 : 0};
+    const StepKey key{R, n_groups, max_count, want_logits ? 1 : 0, n_lrows, 0, e->kernel_timing ? 1 : 0};
     auto it = cache.graphs.find(key);
     if (it == cache.graphs.end()) {
       if (cache.graphs.size() > 512) {  // bounded: drop everything and start over
@@ -359,14 +386,15 @@ int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_
   e->times.n_steps++;
   if (n_lrows > 0) e->times.d2h_bytes += (double)n_lrows * 8 * sizeof(PickOut);
   if (e->kernel_timing) {
-    for (int l = 0; l < L; ++l) {
+    int n_timed = 0;
+    for (int l = 0; l < L; l += XA_TIMED_EVERY, ++n_timed) {
       float t = 0;
       cudaEventElapsedTime(&t, e->xa_ev[2 * l], e->xa_ev[2 * l + 1]);
       e->times.ms_xattn += t;
     }
-    e->times.n_xattn += L;
+    e->times.n_xattn += n_timed;
     // per launch: the cross-KV of every active window once + q in + attention out
-    e->times.xattn_bytes += (double)L * ((double)n_groups * 1500 * 2 * d * 2 + (double)R * d * 4);
+    e->times.xattn_bytes += (double)n_timed * ((double)n_groups * 1500 * 2 * d * 2 + (double)R * d * 4);
   }
   return 0;
 }

@@ -108,7 +108,7 @@ int sw_decode_logits(sw_ctx* ctx, const int32_t* tokens, int n_windows, int n_to
   memset(&cfg, 0, sizeof(cfg));
   for (int pos = 0; pos < n_tok; ++pos) {
     for (int w = 0; w < n_windows; ++w) {
-      e->h_rows.p[w] = DecRow{w, pos, w, 0};
+      e->h_rows.p[w] = DecRow{w, pos, w, pos};
       e->h_tok.p[w] = tokens[(size_t)w * n_tok + pos];
       e->h_pos.p[w] = pos;
       e->h_grp.p[w] = w;

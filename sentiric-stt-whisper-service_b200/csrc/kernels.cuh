@@ -78,17 +78,21 @@ struct DecRow {    // one decoder row of a step
   int slot;        // self-KV slot (page table row)
   int pos;         // position of this token
   int win;         // window index into the cross-KV batch
-  int pad;
+  int pos0;        // first position of this slot whose K/V is produced in this very step: positions
+                   // pos0..pos come from rows r-(pos-pos0)..r of the step (contiguous), older ones from the cache
+  int pages[KV_MAX_PAGES];  // the slot's page list (filled by engine_decode_step from the host page table):
+                            // the attention kernel needs no second dependent lookup
+  int pad[2];
 };
-// append this step's K,V (qkv [R][3d] bf16) to the paged self-KV cache of layer `layer`.
+static_assert(sizeof(DecRow) == 80, "DecRow is uploaded as 20 ints");
 // pool layout: [page][layer][2][KV_PAGE][d]
-int kv_append(const bf16* qkv, const DecRow* d_rows, int R, int d, bf16* pool, const int* d_page_table,
-              int layer, int n_layer, cudaStream_t stream);
 // pool[dst page] = pool[src page] for n pairs (src, dst); page_elems bf16 elements per page
 int kv_copy_pages(bf16* pool, const int* d_pairs, int n, int64_t page_elems, cudaStream_t stream);
-// causal self attention of each row over cache[slot][0..pos]; out [R][d] bf16
-int self_attention(const bf16* qkv, const DecRow* d_rows, int R, int d, int n_head, const bf16* pool,
-                   const int* d_page_table, int layer, int n_layer, bf16* out, cudaStream_t stream);
+// causal self attention of each row over cache[slot][0..pos0) + the K/V this step produces for
+// positions pos0..pos (read from qkv [R][3d] bf16); also appends the row's own K,V to the paged
+// cache of layer `layer` (what kv_append did as a separate launch). out [R][d] bf16
+int self_attention(const bf16* qkv, const DecRow* d_rows, int R, int d, int n_head, bf16* pool,
+                   int layer, int n_layer, bf16* out, cudaStream_t stream);
 // cross attention: q [R][d] bf16; kv = cross-KV of this layer [n_win][T][2d] bf16 (K | V per key).
 // rows must be grouped by window: window g covers rows [grp_start[g], grp_start[g]+grp_count[g]).
 // workspace: f32, >= n_groups*n_chunks*max_cnt*(d + 2*n_head) ... see cross_attention_ws_floats().
@@ -97,7 +101,7 @@ size_t cross_attention_ws_floats(int R, int d, int n_head);
 int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d_grp_win,
                     const int* d_grp_start, const int* d_grp_count, int n_groups, int max_count, int R,
                     int T, int d, int n_head, float* ws, bf16* out, cudaStream_t stream,
-                    cudaEvent_t ev_main_done = nullptr, unsigned ev_flags = 0);
+                    cudaEvent_t ev_main_done = nullptr, unsigned ev_flags = 0);  // event after the main kernel
 
 // weight-streaming GEMM for <= 64-row blocks (skinny_gemm.cu): out = X . W^T
 //   split == 1: out bf16 [R][ldo] = act(acc + bias);   split > 1: partial f32 [split][R][N] (raw sums)

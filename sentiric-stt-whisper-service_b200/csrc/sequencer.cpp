@@ -582,7 +582,7 @@ struct Run {
             set_last_error("self-KV page pool exhausted");
             return -1;
           }
-          e->h_rows.p[R] = DecRow{s, pos, wi, 0};
+          e->h_rows.p[R] = DecRow{s, pos, wi, 0};  // positions 0..pos of this slot are all rows of this step
           e->h_tok.p[R] = w.prompt[pos];
           e->h_pos.p[R] = pos;
           ++R;
@@ -617,7 +617,7 @@ struct Run {
           set_last_error("self-KV page pool exhausted");
           return -1;
         }
-        e->h_rows.p[R] = DecRow{s, pos, wi, 0};
+        e->h_rows.p[R] = DecRow{s, pos, wi, pos};
         e->h_tok.p[R] = w.prompt[pos];
         e->h_pos.p[R] = pos;
         e->h_grp.p[G] = wi;
@@ -833,7 +833,7 @@ struct Run {
             set_last_error("self-KV page pool exhausted");
             return -1;
           }
-          e->h_rows.p[R] = DecRow{s, pos, wi, 0};
+          e->h_rows.p[R] = DecRow{s, pos, wi, pos};
           e->h_tok.p[R] = d.seq.tokens.back().id;
           e->h_pos.p[R] = pos;
           fill_lrow(e->h_lrows.p[n_lr], w, j, R, false);

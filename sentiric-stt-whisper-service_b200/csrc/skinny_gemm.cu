@@ -10,8 +10,16 @@
 // nothing but ldmatrix + mma.sync m16n8k16 (the math is ~1 % of the tensor peak: HBM/L2-bound by
 // construction). Generation 1 issued per-thread cp.async and was instruction-latency bound at
 // ~1 TB/s (profiles/r1_ncu_skinny_v1.txt); per-row 128-byte bulk copies were slower still.
-// N-small matrices are split along K so that >= 2 x 148 CTAs stream weights; split partials are f32
+// N-small matrices are split along K so that >= 148 CTAs stream weights; split partials are f32
 // and are reduced by the consumer (fused LayerNorm / reduce_partials).
+//
+// Tried and rejected, measured with tools/dev_decode_kernels.py (profiles/r1_skinny_ab.log): (a) one
+// persistent CTA per SM with a 16-stage ring: ~2x slower (half the consumer warps per SM); (b) a
+// software-pipelined consumer (fragments of k-block i+1 loaded before the MMAs of k-block i, four
+// accumulator chains): 8.1 vs 6.4 us on QKV, 13.0 vs 9.5 us on FC1. The launch is bound by ring bytes
+// in flight x latency (96 KB per CTA, two thirds of it re-read activations), not by the consumers.
+// The weight tiles of the first ring fill do not depend on the previous kernel, so the producer
+// issues them before griddepcontrol.wait (only matters when SW_PDL=1).
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
@@ -41,6 +49,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_kb = k_slice / SK_BK;
 
+  pdl_launch_dependents();
   if (tid == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
@@ -54,7 +63,16 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
   if (warp == SK_CONSUMERS) {
     if (lane == 0) {
-      for (int kb = 0; kb < n_kb; ++kb) {
+      // weights first (independent of the predecessor), activations once it has finished
+      const int pre = n_kb < SK_STAGES ? n_kb : SK_STAGES;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_arrive_expect_tx(&full[kb], SK_STAGE_BYTES);
+        tma_load_2d(smem + kb * SK_STAGE_BYTES + SK_X_BYTES, &map_w, &full[kb], k_begin + kb * SK_BK, n0);
+      }
+      pdl_wait();
+      for (int kb = 0; kb < pre; ++kb)
+        tma_load_2d(smem + kb * SK_STAGE_BYTES, &map_x, &full[kb], k_begin + kb * SK_BK, r0);
+      for (int kb = pre; kb < n_kb; ++kb) {
         const int s = kb % SK_STAGES;
         const uint32_t ph = (kb / SK_STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
@@ -96,18 +114,19 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (lane == 0) mbar_arrive(&empty[s]);  // every fragment has been consumed: the slot can be refilled
   }
 
+  pdl_wait();  // (already satisfied: the activations we consumed were loaded after the producer's wait)
   const int g = lane >> 2, t4 = lane & 3;
   const int row0 = r0 + rw * 16 + g, row1 = row0 + 8;
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
     const int col = n0 + nh * 16 + nt * 8 + 2 * t4;
     if (col >= N) continue;
+    float v0 = acc[nt][0], v1 = acc[nt][1], v2 = acc[nt][2], v3 = acc[nt][3];
     if (partial) {
       float* p = partial + ((int64_t)blockIdx.y * R) * N;
-      if (row0 < R) *reinterpret_cast<float2*>(p + (int64_t)row0 * N + col) = make_float2(acc[nt][0], acc[nt][1]);
-      if (row1 < R) *reinterpret_cast<float2*>(p + (int64_t)row1 * N + col) = make_float2(acc[nt][2], acc[nt][3]);
+      if (row0 < R) *reinterpret_cast<float2*>(p + (int64_t)row0 * N + col) = make_float2(v0, v1);
+      if (row1 < R) *reinterpret_cast<float2*>(p + (int64_t)row1 * N + col) = make_float2(v2, v3);
     } else {
-      float v0 = acc[nt][0], v1 = acc[nt][1], v2 = acc[nt][2], v3 = acc[nt][3];
       if (bias) {
         const float b0 = __ldg(bias + col), b1 = __ldg(bias + col + 1);
         v0 += b0; v1 += b1; v2 += b0; v3 += b1;
@@ -124,11 +143,13 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 }  // namespace
 
 int skinny_split_for(int N, int K) {
-  // enough CTAs to put two per SM to work; K slices stay multiples of the 64-element k-block
+  // The most CTAs that are still ONE wave at two per SM (a second wave costs a whole CTA lifetime):
+  // the largest divisor of the k-block count with n_blocks * split <= 2 * 148, slices >= 2 k-blocks.
   const int n_blocks = (N + SK_BN - 1) / SK_BN;
+  const int n_kb = K / SK_BK;
   int split = 1;
-  while (n_blocks * split < 2 * 148 && split < 32 && K % (split * 2 * SK_BK) == 0 && K / (split * 2) >= 2 * SK_BK)
-    split *= 2;
+  for (int s = 2; s <= 32 && s <= n_kb / 2; ++s)
+    if (n_kb % s == 0 && n_blocks * s <= 2 * 148) split = s;
   return split;
 }
 
@@ -151,9 +172,8 @@ int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, cons
   if (make_tma_map_2d_bf16(&map_x, X, K, R, ldx, SK_BK, SK_BM)) return -1;
   if (make_tma_map_2d_bf16(&map_w, W, K, N, K, SK_BK, SK_BN)) return -1;
   dim3 grid((N + SK_BN - 1) / SK_BN, split, (R + SK_BM - 1) / SK_BM);
-  skinny_gemm_kernel<<<grid, SK_THREADS, SK_SMEM, stream>>>(map_x, map_w, R, N, k_slice, bias, gelu, out, ldo,
-                                                            partial);
-  SW_CUDA_CHECK(cudaGetLastError());
+  SW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel, grid, dim3(SK_THREADS), SK_SMEM, stream, map_x, map_w, R, N, k_slice,
+                           bias, gelu, out, ldo, partial));
   return 0;
 }
 

@@ -13,6 +13,13 @@
 // dimension holds the <= 8 decoders (beams) that share the window - so the cache is read from HBM
 // once however many beams there are, and no cross-warp merge is needed. Generation 1 did the dot
 // products on CUDA cores and was instruction-issue bound at ~68 % of HBM (profiles/r1_ncu_xattn_v1.txt).
+//
+// The flash-decoding merge of the per-chunk partials is a second, tiny kernel chained by programmatic
+// dependent launch. (Fusing it into this kernel - last-arriving warp merges - was measured at 155 us
+// per launch instead of 79 + combine: the merging warp stalls the two-stage TMA pipeline of its CTA.)
+// The cache does not depend on the previous kernel of the step, so under programmatic dependent
+// launch the producer starts streaming it before griddepcontrol.wait; only the query load and the
+// stores wait.
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
@@ -47,6 +54,7 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_f = d + 2 * n_head;  // floats per (row, chunk) partial
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_kv);
     for (int s = 0; s < n_stages; ++s) {
@@ -58,6 +66,8 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
   __syncthreads();
 
   if (warp == n_cons) {
+    // no pdl_wait here: the cross-KV cache and the group tables were complete before the step's
+    // first kernel started; the loads only fill this CTA's own shared memory
     if (lane == 0) {
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -80,6 +90,7 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
   if (warp > n_cons) return;
 
   // ---- consumers
+  pdl_wait();  // q comes from the previous kernel; ws / out may still be read by earlier ones
   const int g8 = lane >> 2, t4 = lane & 3;
   const float qs = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e), applied to the f32 scores
   // raw query fragments of the next item: [head slot][k-step][a0, a2]
@@ -221,20 +232,17 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
 // Merge the per-chunk partials of a row: one warp per (row, group of 4 heads); lane = (head, 8-dim chunk).
 __global__ void __launch_bounds__(32)
 cross_combine_kernel(const float* __restrict__ ws, int n_chunks, int d, int n_head, bf16* __restrict__ out) {
+  pdl_launch_dependents();
   const int r = blockIdx.x;
   const int h = blockIdx.y * 4 + (threadIdx.x >> 3);
+  pdl_wait();
   if (h >= n_head) return;
   const int c = h * 8 + (threadIdx.x & 7);  // 8-float chunk of the row
   const int row_f = d + 2 * n_head;
   const float* base = ws + (int64_t)r * n_chunks * row_f;
-  float mk[XA_MAX_CHUNKS];
   float M = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < XA_MAX_CHUNKS; ++k)
-    if (k < n_chunks) {
-      mk[k] = base[(int64_t)k * row_f + d + h];
-      M = fmaxf(M, mk[k]);
-    }
+#pragma unroll 8
+  for (int k = 0; k < n_chunks; ++k) M = fmaxf(M, base[(int64_t)k * row_f + d + h]);
   float L = 0.f, a[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) a[e] = 0.f;
@@ -334,9 +342,9 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
       attr_smem = (int)smem;                                                                          \
     }                                                                                                 \
-    cross_attention_kernel<H><<<grid, threads, smem, stream>>>(map, q, d_grp_win, d_grp_start,        \
-                                                               d_grp_count, T, d, n_head, n_cons, spc, \
-                                                               n_stages, n_chunks, n_items, ws);      \
+    SW_CUDA_CHECK(launch_pdl(cross_attention_kernel<H>, dim3(grid), dim3(threads), smem, stream, map, \
+                             q, d_grp_win, d_grp_start, d_grp_count, T, d, n_head, n_cons, spc,        \
+                             n_stages, n_chunks, n_items, ws));                                        \
   } while (0)
   switch (hpw) {
     case 1: XA_LAUNCH(1); break;
@@ -345,10 +353,9 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
     default: set_last_error("cross_attention: unsupported head split"); return -1;
   }
 #undef XA_LAUNCH
-  SW_CUDA_CHECK(cudaGetLastError());
   if (ev_main_done) SW_CUDA_CHECK(cudaEventRecordWithFlags(ev_main_done, stream, ev_flags));
-  cross_combine_kernel<<<dim3(R, (n_head + 3) / 4), 32, 0, stream>>>(ws, n_chunks, d, n_head, out);
-  SW_CUDA_CHECK(cudaGetLastError());
+  SW_CUDA_CHECK(launch_pdl(cross_combine_kernel, dim3(R, (n_head + 3) / 4), dim3(32), 0, stream, ws, n_chunks, d,
+                           n_head, out));
   return 0;
 }
 

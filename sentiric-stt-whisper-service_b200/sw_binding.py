@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsw_whisper.so")
+LIB_PATH = os.environ.get("SW_LIB_PATH") or os.path.join(HERE, "libsw_whisper.so")  # SW_LIB_PATH: A/B a development build
 
 
 class CtxParams(C.Structure):

@@ -4,7 +4,7 @@
 // whisper_decode_internal; the 128-row tcgen05 tiles of gemm_tcgen05.cu leave
 // most SMs idle at these shapes (N/64 CTAs), so the step is bound by how many SMs pull weights.
 //
-// CTA tile 64 (rows) x 32 (weight rows) x 64 (k) per stage, 8-stage smem ring, two CTAs per SM.
+// CTA tile 64 (rows) x BN (32 or 40 weight rows) x 64 (k) per stage, 8-stage smem ring, two CTAs per SM.
 // One producer thread issues two TMA tile loads per stage (128B-swizzled, rows past R / N are
 // zero-filled by the TMA unit) that complete on an mbarrier, so the 8 consumer warps execute
 // nothing but ldmatrix + mma.sync m16n8k16 (the math is ~1 % of the tensor peak: HBM/L2-bound by
@@ -13,13 +13,28 @@
 // N-small matrices are split along K so that >= 148 CTAs stream weights; split partials are f32
 // and are reduced by the consumer (fused LayerNorm / reduce_partials).
 //
+// What bounds a launch (tools/dev_decode_kernels.py, profiles/r1_skinny_shapes.log): a fixed ~3.8 us
+// chain (launch -> first tile -> store) plus the bytes the MOST LOADED SM has to take in through TMA at
+// ~46 B/clk (~88 GB/s): every CTA re-reads its 8 KB activation tile per k-block next to 4-5 KB of
+// weights. 160 CTAs on 148 SMs (FC1 / FC2 with 32-column tiles) put two CTAs on 12 SMs and cost
+// 9.8 us; the same matrix cut into 148 CTAs costs 6.6 us. skinny_plan() therefore picks the tile
+// width (32 or 40 columns) and the K split that minimise the bytes of the most loaded SM:
+// 40 columns x split 4 (128 CTAs) for the d x d and FC2 matrices, 40 x 1 (128 CTAs) for FC1,
+// 32 x 1 (120 CTAs) for QKV. L2-resident weights change nothing (r1_skinny_l2.log): it is SM
+// ingest, not HBM.
 // Tried and rejected, measured with tools/dev_decode_kernels.py (profiles/r1_skinny_ab.log): (a) one
 // persistent CTA per SM with a 16-stage ring: ~2x slower (half the consumer warps per SM); (b) a
 // software-pipelined consumer (fragments of k-block i+1 loaded before the MMAs of k-block i, four
 // accumulator chains): 8.1 vs 6.4 us on QKV, 13.0 vs 9.5 us on FC1. The launch is bound by ring bytes
-// in flight x latency (96 KB per CTA, two thirds of it re-read activations), not by the consumers.
+// in flight x latency (96 KB per CTA, two thirds of it re-read activations), not by the consumers;
+// (c) tcgen05.mma with M = 64, N = 32 and a TMEM accumulator (tools/dev/skinny_gemm_tcgen05_m64.cu.txt,
+// profiles/r1_skinny_tcgen05_m64.log): correct, but 10.8 vs 6.4 us on QKV - tiny SS-mode MMAs are
+// dispatch-latency bound and 16 of 32 lanes per epilogue warp idle.
 // The weight tiles of the first ring fill do not depend on the previous kernel, so the producer
 // issues them before griddepcontrol.wait (only matters when SW_PDL=1).
+#include <math.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
@@ -27,23 +42,31 @@
 namespace sw {
 namespace {
 
-constexpr int SK_BM = 64, SK_BN = 32, SK_BK = 64, SK_STAGES = 8;
-constexpr int SK_X_BYTES = SK_BM * SK_BK * 2, SK_W_BYTES = SK_BN * SK_BK * 2;
-constexpr int SK_STAGE_BYTES = SK_X_BYTES + SK_W_BYTES;
-constexpr int SK_SMEM = SK_STAGES * SK_STAGE_BYTES + 1024 + 2 * SK_STAGES * 8;
+constexpr int SK_BM = 64, SK_BK = 64, SK_STAGES = 8;
+constexpr int SK_X_BYTES = SK_BM * SK_BK * 2;
 constexpr int SK_CONSUMERS = 8;
 constexpr int SK_THREADS = (SK_CONSUMERS + 1) * 32;
+template <int BN>
+struct SkCfg {
+  static constexpr int W_BYTES = BN * SK_BK * 2;
+  static constexpr int STAGE_BYTES = SK_X_BYTES + W_BYTES;  // 12 / 13 KB: stage bases stay 1024-byte aligned
+  static constexpr int SMEM = SK_STAGES * STAGE_BYTES + 1024 + 2 * SK_STAGES * 8;
+  static constexpr int NT = BN / 8;        // 8-column MMA tiles of the CTA
+  static constexpr int NT0 = (NT + 1) / 2;  // tiles of column-warp 0 (column-warp 1 takes the rest)
+};
 
+template <int BN>
 __global__ void __launch_bounds__(SK_THREADS, 2)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, int R,
                    int N, int k_slice, const float* __restrict__ bias, int gelu, bf16* __restrict__ out, int ldo,
                    float* __restrict__ partial) {
+  using C = SkCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t sbase = smem_u32(smem);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SK_STAGES * SK_STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SK_STAGES * C::STAGE_BYTES);
   uint64_t* empty = full + SK_STAGES;
-  const int n0 = blockIdx.x * SK_BN;
+  const int n0 = blockIdx.x * BN;
   const int k_begin = blockIdx.y * k_slice;
   const int r0 = blockIdx.z * SK_BM;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -66,18 +89,18 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       // weights first (independent of the predecessor), activations once it has finished
       const int pre = n_kb < SK_STAGES ? n_kb : SK_STAGES;
       for (int kb = 0; kb < pre; ++kb) {
-        mbar_arrive_expect_tx(&full[kb], SK_STAGE_BYTES);
-        tma_load_2d(smem + kb * SK_STAGE_BYTES + SK_X_BYTES, &map_w, &full[kb], k_begin + kb * SK_BK, n0);
+        mbar_arrive_expect_tx(&full[kb], C::STAGE_BYTES);
+        tma_load_2d(smem + kb * C::STAGE_BYTES + SK_X_BYTES, &map_w, &full[kb], k_begin + kb * SK_BK, n0);
       }
       pdl_wait();
       for (int kb = 0; kb < pre; ++kb)
-        tma_load_2d(smem + kb * SK_STAGE_BYTES, &map_x, &full[kb], k_begin + kb * SK_BK, r0);
+        tma_load_2d(smem + kb * C::STAGE_BYTES, &map_x, &full[kb], k_begin + kb * SK_BK, r0);
       for (int kb = pre; kb < n_kb; ++kb) {
         const int s = kb % SK_STAGES;
         const uint32_t ph = (kb / SK_STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full[s], SK_STAGE_BYTES);
-        uint8_t* xs = smem + s * SK_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
+        uint8_t* xs = smem + s * C::STAGE_BYTES;
         tma_load_2d(xs, &map_x, &full[s], k_begin + kb * SK_BK, r0);
         tma_load_2d(xs + SK_X_BYTES, &map_w, &full[s], k_begin + kb * SK_BK, n0);
       }
@@ -85,31 +108,49 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     return;
   }
 
-  // ---- consumers: warp (rw, nh) owns rows 16*rw.. of the row block and weight rows 16*nh..
+  // ---- consumers: warp (rw, nh) owns rows 16*rw.. of the row block and the 8-column tiles
+  // [t0, t0 + nt) of the CTA (column-warp 0: the first NT0 tiles, column-warp 1: the rest)
   const int rw = warp & 3, nh = warp >> 2;
-  float acc[2][4];
+  const int t0 = nh ? C::NT0 : 0;
+  const int nt_mine = nh ? C::NT - C::NT0 : C::NT0;
+  float acc[C::NT0][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int i = 0; i < C::NT0; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
   // 128B-swizzled tiles: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
   const int a_row = rw * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, a_ch = lane >> 4;
-  const int b_row = nh * 16 + (lane & 7) + (lane >> 4) * 8, b_ch = (lane >> 3) & 1;
+  // weight fragments: x4 = two tiles (rows +0..7 | +8..15, k lo | k hi), x2 = one tile (lanes 0-15 address it)
+  const int b_row4 = t0 * 8 + (lane & 7) + (lane >> 4) * 8;
+  const int b_ch = (lane >> 3) & 1;
   for (int kb = 0; kb < n_kb; ++kb) {
     const int s = kb % SK_STAGES;
     const uint32_t ph = (kb / SK_STAGES) & 1;
     mbar_wait(&full[s], ph);
-    const uint32_t xs = sbase + s * SK_STAGE_BYTES, ws = xs + SK_X_BYTES;
-    uint32_t a[SK_BK / 16][4], b[SK_BK / 16][4];
+    const uint32_t xs = sbase + s * C::STAGE_BYTES, ws = xs + SK_X_BYTES;
+    uint32_t a[SK_BK / 16][4], b[SK_BK / 16][C::NT0][2];
 #pragma unroll
     for (int ks = 0; ks < SK_BK / 16; ++ks) {
       ldmatrix_x4(a[ks], xs + a_row * 128 + (((ks * 2 + a_ch) ^ (a_row & 7)) << 4));
-      ldmatrix_x4(b[ks], ws + b_row * 128 + (((ks * 2 + b_ch) ^ (b_row & 7)) << 4));
+#pragma unroll
+      for (int tp = 0; tp + 1 < C::NT0 + 1; tp += 2) {
+        if (tp + 1 < nt_mine) {  // a pair of tiles
+          uint32_t t[4];
+          const int row = b_row4 + tp * 8;
+          ldmatrix_x4(t, ws + row * 128 + (((ks * 2 + b_ch) ^ (row & 7)) << 4));
+          b[ks][tp][0] = t[0]; b[ks][tp][1] = t[1];
+          if (tp + 1 < C::NT0) { b[ks][tp + 1][0] = t[2]; b[ks][tp + 1][1] = t[3]; }
+        } else if (tp < nt_mine) {  // a last single tile
+          uint32_t t[2];
+          const int row = (t0 + tp) * 8 + (lane & 7);
+          ldmatrix_x2(t, ws + row * 128 + (((ks * 2 + b_ch) ^ (row & 7)) << 4));
+          b[ks][tp][0] = t[0]; b[ks][tp][1] = t[1];
+        }
+      }
     }
 #pragma unroll
-    for (int ks = 0; ks < SK_BK / 16; ++ks) {
-      const uint32_t b01[2] = {b[ks][0], b[ks][1]}, b23[2] = {b[ks][2], b[ks][3]};
-      mma_m16n8k16_bf16(acc[0], a[ks], b01);
-      mma_m16n8k16_bf16(acc[1], a[ks], b23);
-    }
+    for (int ks = 0; ks < SK_BK / 16; ++ks)
+#pragma unroll
+      for (int t = 0; t < C::NT0; ++t)
+        if (t < nt_mine) mma_m16n8k16_bf16(acc[t], a[ks], b[ks][t]);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);  // every fragment has been consumed: the slot can be refilled
   }
@@ -118,15 +159,15 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const int g = lane >> 2, t4 = lane & 3;
   const int row0 = r0 + rw * 16 + g, row1 = row0 + 8;
 #pragma unroll
-  for (int nt = 0; nt < 2; ++nt) {
-    const int col = n0 + nh * 16 + nt * 8 + 2 * t4;
-    if (col >= N) continue;
-    float v0 = acc[nt][0], v1 = acc[nt][1], v2 = acc[nt][2], v3 = acc[nt][3];
+  for (int t = 0; t < C::NT0; ++t) {
+    const int col = n0 + (t0 + t) * 8 + 2 * t4;
+    if (t >= nt_mine || col >= N) continue;
     if (partial) {
       float* p = partial + ((int64_t)blockIdx.y * R) * N;
-      if (row0 < R) *reinterpret_cast<float2*>(p + (int64_t)row0 * N + col) = make_float2(v0, v1);
-      if (row1 < R) *reinterpret_cast<float2*>(p + (int64_t)row1 * N + col) = make_float2(v2, v3);
+      if (row0 < R) *reinterpret_cast<float2*>(p + (int64_t)row0 * N + col) = make_float2(acc[t][0], acc[t][1]);
+      if (row1 < R) *reinterpret_cast<float2*>(p + (int64_t)row1 * N + col) = make_float2(acc[t][2], acc[t][3]);
     } else {
+      float v0 = acc[t][0], v1 = acc[t][1], v2 = acc[t][2], v3 = acc[t][3];
       if (bias) {
         const float b0 = __ldg(bias + col), b1 = __ldg(bias + col + 1);
         v0 += b0; v1 += b1; v2 += b0; v3 += b1;
@@ -140,17 +181,35 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   }
 }
 
+// bytes the most loaded SM takes in for tile width bn and `split` K slices (CTAs dealt round-robin
+// over the SMs, two resident per SM); a third CTA on an SM would be a second wave: excluded
+double sk_cost(int N, int K, int row_blocks, int bn, int split) {
+  const int n_cta = ((N + bn - 1) / bn) * split * row_blocks;
+  if (n_cta > 2 * 148 && split > 1) return 1e30;
+  const double per_cta = (double)(K / split / SK_BK) * (SK_X_BYTES + bn * SK_BK * 2) + 4096.0 * split;
+  return per_cta * ((n_cta + 147) / 148);
+}
+int sk_pick_bn(int N, int K, int row_blocks, int split) {
+  return sk_cost(N, K, row_blocks, 40, split) < sk_cost(N, K, row_blocks, 32, split) ? 40 : 32;
+}
+
 }  // namespace
 
 int skinny_split_for(int N, int K) {
-  // The most CTAs that are still ONE wave at two per SM (a second wave costs a whole CTA lifetime):
-  // the largest divisor of the k-block count with n_blocks * split <= 2 * 148, slices >= 2 k-blocks.
-  const int n_blocks = (N + SK_BN - 1) / SK_BN;
+  // the K split (a divisor of the k-block count, slices of >= 2 k-blocks) that, with the better of the
+  // two tile widths, leaves the fewest bytes on the most loaded SM; ties go to fewer splits
   const int n_kb = K / SK_BK;
-  int split = 1;
-  for (int s = 2; s <= 32 && s <= n_kb / 2; ++s)
-    if (n_kb % s == 0 && n_blocks * s <= 2 * 148) split = s;
-  return split;
+  int best = 1;
+  double best_cost = 1e31;
+  for (int s = 1; s <= 32 && (s == 1 || s <= n_kb / 2); ++s) {
+    if (n_kb % s) continue;
+    const double c = fmin(sk_cost(N, K, 1, 32, s), sk_cost(N, K, 1, 40, s));
+    if (c < best_cost * 0.999) {
+      best_cost = c;
+      best = s;
+    }
+  }
+  return best;
 }
 
 int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, const float* bias, int gelu,
@@ -164,16 +223,24 @@ int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, cons
            "skinny_gemm: operands must be 16-byte aligned");
   static bool attr = false;
   if (!attr) {
-    SW_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
+    SW_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<32>::SMEM));
+    SW_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<40>::SMEM));
     attr = true;
   }
   const int k_slice = K / split;
+  const int row_blocks = (R + SK_BM - 1) / SK_BM;
+  static const int force_bn = getenv("SW_SKINNY_BN") ? atoi(getenv("SW_SKINNY_BN")) : 0;  // development switch
+  const int bn = force_bn ? force_bn : sk_pick_bn(N, K, row_blocks, split);
   CUtensorMap map_x, map_w;
   if (make_tma_map_2d_bf16(&map_x, X, K, R, ldx, SK_BK, SK_BM)) return -1;
-  if (make_tma_map_2d_bf16(&map_w, W, K, N, K, SK_BK, SK_BN)) return -1;
-  dim3 grid((N + SK_BN - 1) / SK_BN, split, (R + SK_BM - 1) / SK_BM);
-  SW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel, grid, dim3(SK_THREADS), SK_SMEM, stream, map_x, map_w, R, N, k_slice,
-                           bias, gelu, out, ldo, partial));
+  if (make_tma_map_2d_bf16(&map_w, W, K, N, K, SK_BK, bn)) return -1;
+  dim3 grid((N + bn - 1) / bn, split, row_blocks);
+  if (bn == 40)
+    SW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<40>, grid, dim3(SK_THREADS), SkCfg<40>::SMEM, stream, map_x, map_w, R,
+                             N, k_slice, bias, gelu, out, ldo, partial));
+  else
+    SW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<32>, grid, dim3(SK_THREADS), SkCfg<32>::SMEM, stream, map_x, map_w, R,
+                             N, k_slice, bias, gelu, out, ldo, partial));
   return 0;
 }
 

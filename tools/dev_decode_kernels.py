@@ -26,7 +26,7 @@ def graph_time(fn, n_in_graph=64, reps=5):
         e1.record(st); st.synchronize()
     return e0.elapsed_time(e1) / (reps * n_in_graph) * 1e3
 
-def run(R, N, K, split, n_w=16):
+def run(R, N, K, split, n_w=int(os.environ.get("N_W", "16"))):
     X = (torch.randn(R, K, device="cuda") * 0.5).bfloat16()
     Ws = [(torch.randn(N, K, device="cuda") * 0.05).bfloat16() for _ in range(n_w)]
     bias = torch.randn(N, device="cuda")
@@ -48,6 +48,11 @@ def run(R, N, K, split, n_w=16):
     print(json.dumps(dict(R=R, N=N, K=K, split=sp, us=round(us, 2), gbs=round(N * K * 2 / us / 1e3, 1), tcgen05_us=round(us2, 2))), flush=True)
 
 d = 1280
+if os.environ.get("SHAPES"):  # "N,K,split;N,K,split;..." at R = 64
+    for t in os.environ["SHAPES"].split(";"):
+        N, K, sp = (int(v) for v in t.split(","))
+        run(64, N, K, sp)
+    sys.exit(0)
 for R in (64, 8):
     for (N, K, sp) in ((3 * d, d, 1), (3 * d, d, 2), (3 * d, d, 4), (d, d, 1), (d, d, 2), (d, d, 4), (4 * d, d, 1), (4 * d, d, 2), (d, 4 * d, 4), (d, 4 * d, 8), (d, 4 * d, 16)):
         run(R, N, K, sp)

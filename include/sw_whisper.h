@@ -47,7 +47,11 @@ typedef struct sw_ctx_params {
   int max_batch;       /* windows decoded together (default 64) */
   int max_beams;       /* decoders per window (default 5) */
   int flash_attn;      /* accepted for API compatibility; always fused */
-  int reserved[12];
+  int n_lanes;         /* independent batches in flight on the device (each lane has its own KV caches,
+                        * activations and stream; the weights are shared). A decoder step is a chain of
+                        * latency-bound kernels around one HBM-bound cross attention, so a second lane fills
+                        * the first one's bubbles. 0 = auto (2 when the second lane's buffers fit), 1, 2. */
+  int reserved[11];
 } sw_ctx_params;
 SW_API sw_ctx_params sw_ctx_default_params(void);
 
@@ -161,6 +165,7 @@ typedef struct sw_stats {
   double ms_xattn;                     /* device time inside cross-attention launches (kernel timing on) */
   long n_xattn;                        /* number of those launches */
   double xattn_bytes;                  /* their algorithmic bytes (cross-KV of the active windows, q, out) */
+  long n_lanes;                        /* lanes of the context; the ms_* above are SUMS over lanes that overlap in time */
 } sw_stats;
 /* bracket every cross-attention launch with CUDA events on the engine's stream (bench roofline) */
 SW_API void sw_ctx_set_kernel_timing(sw_ctx* ctx, int on);

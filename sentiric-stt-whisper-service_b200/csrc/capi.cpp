@@ -1,5 +1,6 @@
 // C ABI (include/sw_whisper.h): the drop-in boundary for the whisper.cpp C API subset that
 // /root/reference/src/stt_engine.cpp binds. No exceptions cross it.
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -43,6 +44,39 @@ sw_ctx* sw_ctx_create(const char* path, const sw_ctx_params* params) {
   if (!e) return nullptr;
   sw_ctx* c = new sw_ctx();
   c->e = e;
+  // further lanes (sw_ctx_params.n_lanes; SW_LANES overrides for experiments). Auto: a second lane when
+  // its buffers fit twice over in what is left of the device memory.
+  int want = params ? params->n_lanes : 0;
+  if (const char* v = getenv("SW_LANES")) want = atoi(v);
+  if (want <= 0) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    want = (e->max_batch >= 2 && free_b > 2 * e->buffer_bytes + (size_t(2) << 30)) ? 2 : 1;
+  }
+  if (want > 4) want = 4;
+  for (int k = 1; k < want; ++k) {
+    Engine* l = sw::engine_create_lane(e);
+    if (!l) {
+      sw::log_msg(3, "lane %d not created (%s): running with %d lane(s)", k, sw_last_error(), k);
+      cudaGetLastError();
+      break;
+    }
+    c->lanes.push_back(l);
+  }
+  if (!c->lanes.empty()) {
+    // several lanes: the persistent cross attention leaves a third of the SMs to the other lanes' small
+    // kernels (large-v3, 2 lanes x 64 windows: 148 CTAs 3033x, 111 3144x, 96 3200x, 80 3140x, 64 2963x RTFx;
+    // profiles/r1_bench_lanes.log). The cache stream stays HBM-bound on 96 SMs.
+    int cap = 0;
+    if (const char* v = getenv("SW_XA_CTAS")) cap = atoi(v);
+    else {
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+      cap = sms * 13 / 20;
+    }
+    e->xa_max_ctas = cap;
+    for (Engine* l : c->lanes) l->xa_max_ctas = cap;
+  }
   return c;
   API_GUARD_END(nullptr)
 }
@@ -52,6 +86,7 @@ void sw_ctx_destroy(sw_ctx* ctx) {
   if (ctx->e) {
     cudaSetDevice(ctx->e->device);
     cudaDeviceSynchronize();
+    for (Engine* l : ctx->lanes) delete l;
     delete ctx->e;
   }
   delete ctx;
@@ -109,7 +144,7 @@ int sw_full_batch_pcm16(sw_ctx* ctx, const sw_full_params* params, const int16_t
     set_last_error("null argument");
     return -1;
   }
-  return sw::run_full_batch(ctx->e, params, reinterpret_cast<const void* const*>(pcm16), n_samples, n, false, out);
+  return sw::run_full_batch_lanes(ctx, params, reinterpret_cast<const void* const*>(pcm16), n_samples, n, false, out);
   API_GUARD_END(-1)
 }
 
@@ -120,7 +155,7 @@ int sw_full_batch_f32(sw_ctx* ctx, const sw_full_params* params, const float* co
     set_last_error("null argument");
     return -1;
   }
-  return sw::run_full_batch(ctx->e, params, reinterpret_cast<const void* const*>(pcm), n_samples, n, true, out);
+  return sw::run_full_batch_lanes(ctx, params, reinterpret_cast<const void* const*>(pcm), n_samples, n, true, out);
   API_GUARD_END(-1)
 }
 
@@ -147,7 +182,9 @@ int sw_result_n_windows(const sw_result* r) { return r ? r->n_windows : 0; }
 void sw_result_free(sw_result* r) { delete r; }
 
 void sw_ctx_set_kernel_timing(sw_ctx* ctx, int on) {
-  if (ctx) ctx->e->kernel_timing = on != 0;
+  if (!ctx) return;
+  ctx->e->kernel_timing = on != 0;
+  for (Engine* l : ctx->lanes) l->kernel_timing = on != 0;
 }
 
 int sw_ctx_get_stats(sw_ctx* ctx, sw_stats* out, int reset) {
@@ -155,14 +192,25 @@ int sw_ctx_get_stats(sw_ctx* ctx, sw_stats* out, int reset) {
     set_last_error("null argument");
     return -1;
   }
-  sw::StageTimes& t = ctx->e->times;
+  sw::StageTimes t = ctx->e->times;
+  for (Engine* l : ctx->lanes) {  // sums over lanes (their device times overlap)
+    const sw::StageTimes& u = l->times;
+    t.ms_mel += u.ms_mel; t.ms_encode += u.ms_encode; t.ms_decode += u.ms_decode;
+    t.n_windows += u.n_windows; t.n_steps += u.n_steps; t.n_launches += u.n_launches;
+    t.decode_bytes += u.decode_bytes; t.h2d_bytes += u.h2d_bytes; t.d2h_bytes += u.d2h_bytes;
+    t.ms_xattn += u.ms_xattn; t.n_xattn += u.n_xattn; t.xattn_bytes += u.xattn_bytes;
+  }
   out->ms_mel = t.ms_mel; out->ms_encode = t.ms_encode; out->ms_decode = t.ms_decode;
   out->n_windows = t.n_windows; out->n_steps = t.n_steps; out->n_launches = t.n_launches;
   out->decode_bytes = t.decode_bytes;
   out->h2d_bytes = t.h2d_bytes; out->d2h_bytes = t.d2h_bytes;
   out->ms_xattn = t.ms_xattn; out->n_xattn = t.n_xattn; out->xattn_bytes = t.xattn_bytes;
   out->decoder_weight_bytes = (double)ctx->e->model->weight_bytes_decoder;
-  if (reset) t = sw::StageTimes();
+  out->n_lanes = 1 + (long)ctx->lanes.size();
+  if (reset) {
+    ctx->e->times = sw::StageTimes();
+    for (Engine* l : ctx->lanes) l->times = sw::StageTimes();
+  }
   return 0;
 }
 

@@ -114,6 +114,18 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Release of a shared-memory stage that was read with ldmatrix: the arrive must not be performed
+// before those reads have returned. Source order is NOT enough: ptxas sees no dependency between
+// LDSM and SYNCS.ARRIVE and scheduled the arrive of the 32-column skinny GEMM right behind the issue
+// of the last LDSM, ahead of the HMMAs that consume them; under SM contention (a second lane) the
+// producer's next TMA write then landed in the slot before a late LDSM had read it - one warp of one
+// CTA computed a k-block from the wrong tile about once in 500 launches (tools/dev_determinism5.py).
+// `dep` is a value computed from one result register of every ldmatrix of the stage and `zero` a
+// run-time zero (kernel argument) the compiler cannot fold: the barrier address now depends on the
+// loads, so the arrive cannot issue until they have completed.
+__device__ __forceinline__ void mbar_arrive_after_reads(uint64_t* bar, uint32_t dep, uint32_t zero) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar) + (dep & zero)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                "r"(bytes)

@@ -34,10 +34,10 @@ Engine::~Engine() {
     if (ev) cudaEventDestroy(ev);
   engine_free_step_graphs(this);
   if (stream) cudaStreamDestroy(stream);
-  delete model;
+  if (owns_model) delete model;
 }
 
-static int engine_init(Engine* e, const char* path, const sw_ctx_params* p) {
+static int engine_init(Engine* e, const char* path, const sw_ctx_params* p, const Engine* primary) {
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
     cudaGetLastError();
@@ -60,8 +60,15 @@ static int engine_init(Engine* e, const char* path, const sw_ctx_params* p) {
     const char* g = getenv("SW_GRAPHS");  // development switch: SW_GRAPHS=0 launches the step kernel by kernel
     e->use_graphs = !(g && strcmp(g, "0") == 0);
   }
-  e->model = load_model(path);
-  if (!e->model) return -1;
+  size_t free0 = 0, total0 = 0;
+  if (primary) {
+    e->model = primary->model;
+    e->owns_model = false;
+  } else {
+    e->model = load_model(path);
+    if (!e->model) return -1;
+  }
+  cudaMemGetInfo(&free0, &total0);
   SW_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   SW_CUDA_CHECK(cudaEventCreate(&e->ev0));
   SW_CUDA_CHECK(cudaEventCreate(&e->ev1));
@@ -97,7 +104,13 @@ static int engine_init(Engine* e, const char* path, const sw_ctx_params* p) {
       e->h_grp.alloc(3 * R) || e->h_rows.alloc(R) || e->h_lrows.alloc(R) || e->h_picks.alloc(R * 8))
     return -1;
   SW_CUDA_CHECK(cudaDeviceSynchronize());
-  log_msg(2, "model loaded: d=%d layers=%d/%d n_mels=%d n_vocab=%d; max_batch=%d max_beams=%d",
+  {
+    size_t free1 = 0, total1 = 0;
+    cudaMemGetInfo(&free1, &total1);
+    e->buffer_bytes = free0 > free1 ? free0 - free1 : 0;
+  }
+  if (!primary)
+    log_msg(2, "model loaded: d=%d layers=%d/%d n_mels=%d n_vocab=%d; max_batch=%d max_beams=%d",
           hp.n_audio_state, hp.n_audio_layer, hp.n_text_layer, hp.n_mels, hp.n_vocab, e->max_batch,
           e->max_beams);
   return 0;
@@ -105,7 +118,21 @@ static int engine_init(Engine* e, const char* path, const sw_ctx_params* p) {
 
 Engine* engine_create(const char* model_path, const sw_ctx_params* params) {
   Engine* e = new Engine();
-  if (engine_init(e, model_path, params)) {
+  if (engine_init(e, model_path, params, nullptr)) {
+    delete e;
+    return nullptr;
+  }
+  return e;
+}
+
+Engine* engine_create_lane(const Engine* primary) {
+  sw_ctx_params p;
+  memset(&p, 0, sizeof(p));
+  p.device = primary->device;
+  p.max_batch = primary->max_batch;
+  p.max_beams = primary->max_beams;
+  Engine* e = new Engine();
+  if (engine_init(e, nullptr, &p, primary)) {
     delete e;
     return nullptr;
   }
@@ -272,7 +299,7 @@ static int enqueue_decode_step(Engine* e, int R, int n_groups, int max_count, bo
     if (!(skip & 64)) {
       if (cross_attention(e->dq.p, e->cross_kv.p + l * layer_stride, (int64_t)e->max_batch * 1500, e->d_grp_win.p,
                           e->d_grp_start.p, e->d_grp_count.p, n_groups, max_count, R, 1500, d, hp.n_text_head,
-                          e->xa_ws.p, e->datt.p, st, timed ? e->xa_ev[2 * l + 1] : nullptr, ev_flags))
+                          e->xa_ws.p, e->datt.p, st, timed ? e->xa_ev[2 * l + 1] : nullptr, ev_flags, e->xa_max_ctas))
         return -1;
       *launches += 2;
     } else if (timed) {

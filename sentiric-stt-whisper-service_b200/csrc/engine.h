@@ -62,6 +62,10 @@ struct Engine {
   int device = 0;
   int max_batch = 64, max_beams = 5, max_rows = 320;
   Model* model = nullptr;
+  bool owns_model = true;   // false for the further lanes of a context (they share lane 0's weights)
+  int xa_max_ctas = 0;      // cap on the persistent cross-attention grid (0 = every SM); contexts with
+                            // several lanes leave SMs to the other lane's latency-bound kernels
+  size_t buffer_bytes = 0;  // device memory of this lane's buffers (without the weights)
   cudaStream_t stream = nullptr;
   std::mutex mu;  // one batch in flight per context
 
@@ -110,6 +114,8 @@ struct Engine {
 };
 
 Engine* engine_create(const char* model_path, const sw_ctx_params* params);
+// a further lane next to `primary`: same model (shared, not owned), same limits, own buffers and stream
+Engine* engine_create_lane(const Engine* primary);
 
 // conv stem + encoder stack + ln_post + cross-KV for n_win windows whose conv input is in conv_in.
 // enc_out_f32 (device, [n_win*1500][d]) may be null.

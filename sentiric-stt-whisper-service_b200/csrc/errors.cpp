@@ -20,6 +20,8 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+const char* last_error_string() { return g_err; }
+
 void log_msg(int level, const char* fmt, ...) {
   char buf[1024];
   va_list ap;

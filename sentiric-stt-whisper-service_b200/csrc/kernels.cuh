@@ -101,7 +101,8 @@ size_t cross_attention_ws_floats(int R, int d, int n_head);
 int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d_grp_win,
                     const int* d_grp_start, const int* d_grp_count, int n_groups, int max_count, int R,
                     int T, int d, int n_head, float* ws, bf16* out, cudaStream_t stream,
-                    cudaEvent_t ev_main_done = nullptr, unsigned ev_flags = 0);  // event after the main kernel
+                    cudaEvent_t ev_main_done = nullptr, unsigned ev_flags = 0,  // event after the main kernel
+                    int max_ctas = 0);  // cap on the persistent grid (0 = one CTA per SM)
 
 // weight-streaming GEMM for <= 64-row blocks (skinny_gemm.cu): out = X . W^T
 //   split == 1: out bf16 [R][ldo] = act(acc + bias);   split > 1: partial f32 [split][R][N] (raw sums)

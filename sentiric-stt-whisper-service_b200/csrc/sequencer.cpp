@@ -1147,4 +1147,56 @@ int run_full_batch(Engine* e, const sw_full_params* params, const void* const* p
   return rc;
 }
 
+int run_full_batch_lanes(sw_ctx* ctx, const sw_full_params* params, const void* const* pcm, const int* n_samples,
+                         int n, bool is_f32, sw_result** out) {
+  SW_CHECK(ctx && ctx->e && params && out && n > 0, "bad arguments");
+  const int n_lanes = 1 + (int)ctx->lanes.size();
+  if (n_lanes == 1 || n < 2) return run_full_batch(ctx->e, params, pcm, n_samples, n, is_f32, out);
+  // deal the utterances: lane k takes every n_lanes-th one, so ragged lengths spread evenly
+  struct LaneJob {
+    std::vector<const void*> pcm;
+    std::vector<int> n_samples, index;
+    std::vector<sw_result*> out;
+    int rc = 0;
+    std::string err;
+  };
+  std::vector<LaneJob> jobs(n_lanes);
+  for (int i = 0; i < n; ++i) {
+    LaneJob& j = jobs[i % n_lanes];
+    j.pcm.push_back(pcm[i]);
+    j.n_samples.push_back(n_samples[i]);
+    j.index.push_back(i);
+  }
+  auto work = [&](int k) {
+    LaneJob& j = jobs[k];
+    if (j.index.empty()) return;
+    j.out.assign(j.index.size(), nullptr);
+    Engine* e = k == 0 ? ctx->e : ctx->lanes[k - 1];
+    try {
+      j.rc = run_full_batch(e, params, j.pcm.data(), j.n_samples.data(), (int)j.index.size(), is_f32, j.out.data());
+    } catch (const std::exception& ex) {
+      set_last_error("internal error: %s", ex.what());
+      j.rc = -1;
+    }
+    if (j.rc) j.err = last_error_string();  // the error string is thread-local: hand it to the caller
+  };
+  std::vector<std::thread> th;
+  for (int k = 1; k < n_lanes; ++k) th.emplace_back(work, k);
+  work(0);
+  for (auto& t : th) t.join();
+  int rc = 0;
+  for (auto& j : jobs)
+    if (j.rc && !rc) {
+      rc = j.rc;
+      set_last_error("%s", j.err.c_str());
+    }
+  for (int i = 0; i < n; ++i) out[i] = nullptr;
+  for (auto& j : jobs)
+    for (size_t q = 0; q < j.out.size(); ++q) {
+      if (rc) delete j.out[q];
+      else out[j.index[q]] = j.out[q];
+    }
+  return rc;
+}
+
 }  // namespace sw

@@ -6,7 +6,8 @@
 #include "engine.h"
 
 struct sw_ctx {
-  sw::Engine* e = nullptr;
+  sw::Engine* e = nullptr;            // lane 0: owns the model; the stage hooks run here
+  std::vector<sw::Engine*> lanes;     // further lanes: own buffers and stream, weights shared with e
 };
 struct sw_segment {
   int64_t t0 = 0, t1 = 0;
@@ -26,4 +27,9 @@ namespace sw {
 // Returns 0, or non-zero on failure/abort (all out[i] are null then).
 int run_full_batch(Engine* e, const sw_full_params* params, const void* const* pcm, const int* n_samples,
                    int n, bool is_f32, sw_result** out);
+// The same over all lanes of a context: utterances are dealt to the lanes (they are independent units,
+// SURVEY.md §8e), one host thread per lane drives its engine, results land in the caller's order.
+int run_full_batch_lanes(sw_ctx* ctx, const sw_full_params* params, const void* const* pcm, const int* n_samples,
+                         int n, bool is_f32, sw_result** out);
+const char* last_error_string();
 }  // namespace sw

@@ -59,7 +59,7 @@ template <int BN>
 __global__ void __launch_bounds__(SK_THREADS, 2)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, int R,
                    int N, int k_slice, const float* __restrict__ bias, int gelu, bf16* __restrict__ out, int ldo,
-                   float* __restrict__ partial) {
+                   float* __restrict__ partial, uint32_t zero) {
   using C = SkCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -127,9 +127,11 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     mbar_wait(&full[s], ph);
     const uint32_t xs = sbase + s * C::STAGE_BYTES, ws = xs + SK_X_BYTES;
     uint32_t a[SK_BK / 16][4], b[SK_BK / 16][C::NT0][2];
+    uint32_t dep = 0;  // one result register of every ldmatrix of this stage (mbar_arrive_after_reads)
 #pragma unroll
     for (int ks = 0; ks < SK_BK / 16; ++ks) {
       ldmatrix_x4(a[ks], xs + a_row * 128 + (((ks * 2 + a_ch) ^ (a_row & 7)) << 4));
+      dep ^= a[ks][0];
 #pragma unroll
       for (int tp = 0; tp + 1 < C::NT0 + 1; tp += 2) {
         if (tp + 1 < nt_mine) {  // a pair of tiles
@@ -138,11 +140,13 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           ldmatrix_x4(t, ws + row * 128 + (((ks * 2 + b_ch) ^ (row & 7)) << 4));
           b[ks][tp][0] = t[0]; b[ks][tp][1] = t[1];
           if (tp + 1 < C::NT0) { b[ks][tp + 1][0] = t[2]; b[ks][tp + 1][1] = t[3]; }
+          dep ^= t[0];
         } else if (tp < nt_mine) {  // a last single tile
           uint32_t t[2];
           const int row = (t0 + tp) * 8 + (lane & 7);
           ldmatrix_x2(t, ws + row * 128 + (((ks * 2 + b_ch) ^ (row & 7)) << 4));
           b[ks][tp][0] = t[0]; b[ks][tp][1] = t[1];
+          dep ^= t[0];
         }
       }
     }
@@ -152,7 +156,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       for (int t = 0; t < C::NT0; ++t)
         if (t < nt_mine) mma_m16n8k16_bf16(acc[t], a[ks], b[ks][t]);
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);  // every fragment has been consumed: the slot can be refilled
+    if (lane == 0) mbar_arrive_after_reads(&empty[s], dep, zero);  // every fragment is in registers: the slot can be refilled
   }
 
   pdl_wait();  // (already satisfied: the activations we consumed were loaded after the producer's wait)
@@ -237,10 +241,10 @@ int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, cons
   dim3 grid((N + bn - 1) / bn, split, row_blocks);
   if (bn == 40)
     SW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<40>, grid, dim3(SK_THREADS), SkCfg<40>::SMEM, stream, map_x, map_w, R,
-                             N, k_slice, bias, gelu, out, ldo, partial));
+                             N, k_slice, bias, gelu, out, ldo, partial, 0u));
   else
     SW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<32>, grid, dim3(SK_THREADS), SkCfg<32>::SMEM, stream, map_x, map_w, R,
-                             N, k_slice, bias, gelu, out, ldo, partial));
+                             N, k_slice, bias, gelu, out, ldo, partial, 0u));
   return 0;
 }
 

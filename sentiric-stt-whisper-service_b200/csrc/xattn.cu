@@ -43,7 +43,7 @@ __global__ void __launch_bounds__((XA_MAX_CONSUMERS + 1) * 32, 1)
 cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* __restrict__ q,
                        const int* __restrict__ grp_win, const int* __restrict__ grp_start,
                        const int* __restrict__ grp_count, int T, int d, int n_head, int n_cons, int spc,
-                       int n_stages, int n_chunks, int n_items, float* __restrict__ ws) {
+                       int n_stages, int n_chunks, int n_items, float* __restrict__ ws, uint32_t zero) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -142,6 +142,7 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
       mbar_wait(&full[s], ph);
       const uint32_t st = sbase + s * stage_bytes;
       const int nk = min(XA_KEYS, key_end - key_begin - i * XA_KEYS);
+      uint32_t dep = 0;  // one result register of every ldmatrix of this stage (mbar_arrive_after_reads)
 #pragma unroll
       for (int hs = 0; hs < HPW; ++hs) {
         const int h = warp + hs * n_cons;
@@ -156,6 +157,7 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
           const int key = (lane & 7) + (lane >> 4) * 8;
           const int ch = ks * 2 + ((lane >> 3) & 1);
           ldmatrix_x4(b, kt + key * 128 + ((ch ^ (key & 7)) << 4));
+          dep ^= b[0];
           const uint32_t b01[2] = {b[0], b[1]}, b23[2] = {b[2], b[3]};
           mma_m16n8k16_bf16(sc[0], qa[hs][ks], b01);
           mma_m16n8k16_bf16(sc[1], qa[hs][ks], b23);
@@ -193,6 +195,7 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
           const int key = (lane & 7) + ((lane >> 3) & 1) * 8;
           const int ch = dp * 2 + (lane >> 4);
           ldmatrix_x4_trans(b, vt + key * 128 + ((ch ^ (key & 7)) << 4));
+          dep ^= b[0];
           const uint32_t b01[2] = {b[0], b[1]}, b23[2] = {b[2], b[3]};
           float acc0[4] = {o[hs][2 * dp][0], o[hs][2 * dp][1], 0.f, 0.f};
           float acc1[4] = {o[hs][2 * dp + 1][0], o[hs][2 * dp + 1][1], 0.f, 0.f};
@@ -205,7 +208,7 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
+      if (lane == 0) mbar_arrive_after_reads(&empty[s], dep, zero);
     }
     // ---- partial result of this (window, chunk): unnormalised O, running max m and sum l per head
 #pragma unroll
@@ -274,9 +277,10 @@ int xa_num_sms() {
 }
 
 // stages per work item: the value that leaves the fewest idle SM-slots in the last wave
-void xa_plan(int n_groups, int T, int d, int* spc_out, int* n_chunks, int* n_stages, int* grid) {
+void xa_plan(int n_groups, int T, int d, int max_ctas, int* spc_out, int* n_chunks, int* n_stages, int* grid) {
   const int total_stages = (T + XA_KEYS - 1) / XA_KEYS;
-  const int sms = xa_num_sms();
+  int sms = xa_num_sms();
+  if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
   int best_spc = 3;
   double best_eff = -1.0;
   for (int spc = 3; spc <= 16; ++spc) {
@@ -311,7 +315,7 @@ size_t cross_attention_ws_floats(int R, int d, int n_head) {
 int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d_grp_win,
                     const int* d_grp_start, const int* d_grp_count, int n_groups, int max_count, int R,
                     int T, int d, int n_head, float* ws, bf16* out, cudaStream_t stream,
-                    cudaEvent_t ev_main_done, unsigned ev_flags) {
+                    cudaEvent_t ev_main_done, unsigned ev_flags, int max_ctas) {
   if (n_groups <= 0 || R <= 0) return 0;
   SW_CHECK(d == n_head * 64, "cross_attention: head dim must be 64");
   SW_CHECK(max_count >= 1 && max_count <= 8, "cross_attention: group of %d rows", max_count);
@@ -322,7 +326,7 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
   const int hpw = n_head / n_cons;
   SW_CHECK(hpw <= XA_MAX_HPW, "cross_attention: %d heads per warp", hpw);
   int spc, n_chunks, n_stages, grid;
-  xa_plan(n_groups, T, d, &spc, &n_chunks, &n_stages, &grid);
+  xa_plan(n_groups, T, d, max_ctas, &spc, &n_chunks, &n_stages, &grid);
   const int stage_bytes = XA_KEYS * 2 * d * 2;
   const size_t smem = (size_t)n_stages * stage_bytes + 1024 + 2 * n_stages * sizeof(uint64_t);
   SW_CHECK(smem <= 227 * 1024, "cross_attention: %zu bytes of shared memory", smem);
@@ -344,7 +348,7 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
     }                                                                                                 \
     SW_CUDA_CHECK(launch_pdl(cross_attention_kernel<H>, dim3(grid), dim3(threads), smem, stream, map, \
                              q, d_grp_win, d_grp_start, d_grp_count, T, d, n_head, n_cons, spc,        \
-                             n_stages, n_chunks, n_items, ws));                                        \
+                             n_stages, n_chunks, n_items, ws, 0u));                                    \
   } while (0)
   switch (hpw) {
     case 1: XA_LAUNCH(1); break;

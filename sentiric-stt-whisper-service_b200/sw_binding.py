@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("SW_LIB_PATH") or os.path.join(HERE, "libsw_whisper.so
 
 class CtxParams(C.Structure):
     _fields_ = [("device", C.c_int), ("max_batch", C.c_int), ("max_beams", C.c_int),
-                ("flash_attn", C.c_int), ("reserved", C.c_int * 12)]
+                ("flash_attn", C.c_int), ("n_lanes", C.c_int), ("reserved", C.c_int * 11)]
 
 
 class ModelInfo(C.Structure):
@@ -55,7 +55,7 @@ class Stats(C.Structure):
                 ("n_windows", C.c_long), ("n_steps", C.c_long), ("n_launches", C.c_long),
                 ("decode_bytes", C.c_double), ("decoder_weight_bytes", C.c_double),
                 ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double), ("ms_xattn", C.c_double),
-                ("n_xattn", C.c_long), ("xattn_bytes", C.c_double)]
+                ("n_xattn", C.c_long), ("xattn_bytes", C.c_double), ("n_lanes", C.c_long)]
 
 
 EXPORTS = [
@@ -141,10 +141,10 @@ def _tok(t):
 
 
 class Engine:
-    def __init__(self, model_path, device=0, max_batch=64, max_beams=5):
+    def __init__(self, model_path, device=0, max_batch=64, max_beams=5, n_lanes=0):
         self.L = lib()
         p = self.L.sw_ctx_default_params()
-        p.device, p.max_batch, p.max_beams = device, max_batch, max_beams
+        p.device, p.max_batch, p.max_beams, p.n_lanes = device, max_batch, max_beams, n_lanes
         self.h = self.L.sw_ctx_create(model_path.encode(), C.byref(p))
         if not self.h:
             raise RuntimeError("sw_ctx_create: " + last_error())

@@ -308,3 +308,123 @@ def test_config2_base_batch32_properties(swb, ora):
     st = e.stats()
     assert st["n_launches"] > 0 and st["n_windows"] == 32
     e.close()
+
+
+def test_lanes_do_not_change_results(swb, tiny_model):
+    """A context with two lanes (two batches in flight, utterances dealt to the lanes) returns exactly
+    what a one-lane context returns (same tokens, texts, times): utterances are independent units
+    (SURVEY.md §8e)."""
+    clips = [synth_audio.utterance(6, i, seconds=s) for i, s in
+             enumerate([30.0, 4.0, 17.5, 30.0, 9.0, 41.5, 0.4, 12.0, 30.0, 2.0, 26.0])]
+    outs = []
+    for lanes in (1, 2):
+        e = swb.Engine(tiny_model[0], max_batch=4, max_beams=5, n_lanes=lanes)
+        assert e.stats()["n_lanes"] == lanes
+        outs.append(e.full_batch_pcm16(clips, e.default_params(0, **GREEDY)))
+        kw = dict(language="en", temperature_inc=0.0, suppress_nst=1, beam_size=5)
+        outs.append(e.full_batch_pcm16(clips[:5], e.default_params(1, **kw)))
+        e.close()
+    # the lanes cut the utterances into different sub-batches, which changes the split of the cross
+    # attention keys (summation order, then bf16 roundings): tokens, texts and times are identical, p agrees to 1e-2
+    for a, b in zip(outs[0], outs[2]):  # greedy
+        compare_results(a, b)
+    for a, b in zip(outs[1], outs[3]):  # beam search
+        compare_results(a, b)
+
+
+def test_config3_small_beam5_paged_kv_properties(swb, ora):
+    """BASELINE configs[2]: Whisper small widths (d = 768, 12 heads; 4 of the 12 layers so that the seeded
+    file stays small), beam search with 5 beams over the paged self-KV cache, 32 x 30 s windows.
+    Size-independent properties: every window follows the scripted transcript, a duplicate inside the
+    batch is bit-identical, a rerun is bit-identical (page reshuffles leave no state behind), segment
+    times tile the window; two windows are compared token by token with the bf16-mode oracle."""
+    path, info = model_file("small-4l", script_len=48)
+    e = swb.Engine(path, max_batch=32, max_beams=5)
+    clips = [synth_audio.utterance(3, i) for i in range(31)] + [synth_audio.utterance(3, 0)]
+    kw = dict(language="en", temperature_inc=0.0, suppress_nst=1, beam_size=5)
+    pe = e.default_params(1, **kw)
+    got = e.full_batch_pcm16(clips, pe)
+    again = e.full_batch_pcm16(clips, pe)
+    assert got == again
+    assert got[0] == got[31]
+    sp, script = info["special"], info["script"]
+    kept = [t for i, t in enumerate(script[:-1]) if not (i > 0 and t >= sp["beg"] and script[i - 1] == t)]
+    assert sum(seg_ids(g) == kept for g in got) >= 31
+    for g in got:
+        assert g["segments"][0]["t0"] == 0 and g["segments"][-1]["t1"] == 3000
+    ob = ora.Oracle(path, weight_round=True, act_round=ora.ACT_BF16)
+    for i in (5, 22):
+        want = ob.full(synth_audio.to_f32(clips[i]), ob.default_params(1, **kw))
+        assert seg_ids(got[i]) == seg_ids(want)
+    e.close()
+
+
+def test_config4_medium_multilingual_ragged_properties(swb, ora):
+    """BASELINE configs[3]: Whisper medium widths (d = 1024, 16 heads; 3 of the 24 layers), multilingual,
+    utterances of mixed 5-30 s length with the language cycled over en/tr/de/ja; the 2-GPU sharding of
+    this configuration is the world_size-2 gloo test in test_host_logic.py. Properties: results do not
+    depend on what else is in the batch (ragged neighbours, other languages), the language token of the
+    prompt changes the result's lang_id, segment times stay inside the utterance; one utterance per
+    of two languages is compared with the oracle."""
+    path, info = model_file("medium-3l", script_len=32)
+    e = swb.Engine(path, max_batch=16, max_beams=5)
+    langs = ["en", "tr", "de", "ja"]
+    rng = np.random.default_rng(4)
+    secs = [round(float(rng.uniform(5, 30)), 2) for _ in range(24)]
+    clips = [synth_audio.utterance(4, i, seconds=s) for i, s in enumerate(secs)]
+    by_lang = {}
+    for li, lang in enumerate(langs):
+        pe = e.default_params(0, **dict(GREEDY, language=lang))
+        idx = [i for i in range(24) if i % 4 == li]
+        res = e.full_batch_pcm16([clips[i] for i in idx], pe)
+        for i, r in zip(idx, res):
+            by_lang[i] = r
+            assert r["lang_id"] == swb.lib().sw_lang_id(lang.encode())
+            for s in r["segments"]:
+                assert 0 <= s["t0"] <= s["t1"] <= 3000
+        alone = e.full_batch_pcm16([clips[idx[2]]], pe)[0]
+        compare_results(alone, res[2])  # what else is in the batch does not change tokens or times
+    o = ora.Oracle(path, weight_round=False, act_round=ora.ACT_F16)
+    for li, lang in ((0, "en"), (3, "ja")):
+        i = li  # utterance li was decoded with language li
+        want = o.full(synth_audio.to_f32(clips[i]), o.default_params(0, **dict(GREEDY, language=lang)))
+        compare_results(by_lang[i], want)
+    e.close()
+
+
+def test_decode_is_bit_deterministic_under_concurrent_load(swb, tiny_model):
+    """Regression test for a stage-release race: the skinny GEMM released its shared-memory stage with an
+    mbarrier arrive that ptxas had scheduled ahead of the completion of the last ldmatrix, so that under
+    SM contention (a second engine or lane on the same GPU) the next TMA write could land before a late
+    read and one warp computed a k-block from the wrong tile (about one launch in 500). The
+    teacher-forced logits and a whole beam-search transcription must be bit-identical across repeats
+    while another engine keeps the GPU busy from a second host thread."""
+    import threading
+    a = swb.Engine(tiny_model[0], max_batch=16, max_beams=5, n_lanes=1)
+    b = swb.Engine(tiny_model[0], max_batch=16, max_beams=5, n_lanes=1)
+    clips = [synth_audio.utterance(7, i, seconds=10.0 + i) for i in range(12)]
+    pb = b.default_params(0, **GREEDY)
+    tok = np.random.default_rng(3).integers(0, 50000, size=(16, 16)).astype(np.int32)
+    kw = dict(language="en", temperature_inc=0.0, suppress_nst=1, beam_size=5)
+    ref_beam = a.full_batch_pcm16(clips[:6], a.default_params(1, **kw))
+    ref_logits = a.decode_logits(tok)  # teacher-forced over the cross-KV the run above left behind
+    stop = []
+
+    def hammer():
+        while not stop:
+            b.full_batch_pcm16(clips, pb)
+
+    th = threading.Thread(target=hammer)
+    th.start()
+    try:
+        for _ in range(10):
+            assert np.array_equal(a.decode_logits(tok), ref_logits)
+        from tools.dev_determinism import diff
+        for _ in range(3):
+            d = diff(ref_beam, a.full_batch_pcm16(clips[:6], a.default_params(1, **kw)))
+            assert not d, d[:6]
+    finally:
+        stop.append(1)
+        th.join()
+    a.close()
+    b.close()

@@ -35,6 +35,8 @@ SIZES = {
     "small":    (768, 12, 12, 80, 51865),
     "medium":   (1024, 16, 24, 80, 51865),
     "large-v3": (1280, 20, 32, 128, 51866),
+    "small-4l":  (768, 12, 4, 80, 51865),    # small / medium widths at reduced depth: config 3 / 4 property tests
+    "medium-3l": (1024, 16, 3, 80, 51865),
     "large-v3-2l": (1280, 20, 2, 128, 51866),  # large-v3 widths, 2 layers: kernel profiling without the 3 GB file
     "large-v3-8l": (1280, 20, 8, 128, 51866),  # 8 layers: per-layer decoder-step time without the 3 GB file
 }

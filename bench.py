@@ -10,7 +10,8 @@ over 8 GPUs), synthetic 16 kHz speech-like audio, seeded synthetic ggml weights 
 follows a scripted ~100-token timestamped transcript. One "step" = one pass of the whole hot
 path (PCM -> log-mel -> conv stem -> encoder -> cross-KV -> greedy decode -> segments) over the
 rank's 128 windows. Windows are independent: ranks share nothing (weak scaling, no collective on
-the data path); torch.distributed is used only for the barrier and the max-over-ranks time.
+the data path); torch.distributed is used only for the barrier and the max-over-ranks time. The context
+runs two lanes (two batches of 64 windows in flight on the GPU, weights shared; `stages.lanes`).
 
 `value` : audio-seconds per second with the PCM already resident in HBM (device pointers in).
 `e2e`   : the same through the reference-facing C-ABI call with pinned HOST buffers (H2D of the

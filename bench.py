@@ -287,6 +287,8 @@ def main():
             decode_steps=int(st["n_steps"] / args.steps),
             device_ms_per_step=dict(mel=st["ms_mel"] / args.steps, encode=st["ms_encode"] / args.steps,
                                     decode=st["ms_decode"] / args.steps),
+            frontend_gbs=(480000 * 2 + nm * 3000 * 4) * W * args.steps / max(1e-9, st["ms_mel"] * 1e-3) / 1e9,
+            frontend_note="(int16 PCM in + f32 log-mel out) / device time of the front end (mel + token-timestamp energy kernels, uploads)",
             encoder_ms_per_window=st["ms_encode"] / max(1, st["n_windows"]),
             encoder_tflops=enc_tf, encoder_frac_of_sustained_peak=enc_tf / pk["tf_sust"],
             decode_gbs=dec_gbs, decode_frac_of_hbm=dec_gbs / pk["hbm"]))

@@ -41,7 +41,7 @@ int mel_hook(Engine* e, const void* pcm, int n_samples, bool is_f32, float* out,
   memcpy(&b, &neg10, 4);
   b = ~b;
   SW_CUDA_CHECK(cudaMemcpyAsync(d_max.p, &b, 4, cudaMemcpyHostToDevice, st));
-  if (mel_log_power(d_pcm.p, is_f32, d_utt.p, 1, mu.n_active, m.filters, n_mel, d_log.p, d_max.p, st)) return -1;
+  if (mel_log_power(d_pcm.p, is_f32, d_utt.p, 1, mu.n_active, m.filters, m.filter_span, n_mel, d_log.p, d_max.p, st)) return -1;
   if (mel_finalize_full(d_log.p, d_utt.p, d_max.p, 0, n_mel, mu.n_len, mu.n_active, d_out.p, st)) return -1;
   SW_CUDA_CHECK(cudaMemcpyAsync(out, d_out.p, (size_t)n_mel * mu.n_len * 4, cudaMemcpyDeviceToHost, st));
   SW_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -26,9 +26,10 @@ struct MelUtt {            // one utterance, device-side descriptor
 };
 // log10 mel power of every active frame (before clamp/normalise) + per-utterance max.
 // pcm is int16 (is_f32 = 0, scaled by 1/32768 in-register) or f32.
+// d_filter_span[m] = {first bin rounded down to a multiple of 4, one past the last bin} with a non-zero weight
 int mel_log_power(const void* pcm, int is_f32, const MelUtt* d_utts, int n_utts, int max_active,
-                  const float* d_filters, int n_mel, float* d_log, unsigned* d_max_enc,
-                  cudaStream_t stream);
+                  const float* d_filters, const int2* d_filter_span, int n_mel, float* d_log,
+                  unsigned* d_max_enc, cudaStream_t stream);
 // clamp to max-8, (x+4)/4; window w reads utterance win_utt[w] at frame win_seek[w].
 //   out_bf16: [n_win][3002][n_mel] time-major, rows 0 and 3001 zero (conv1's implicit-GEMM input)
 //   out_f32 : [n_win][n_mel][3000] mel-major (may be null)

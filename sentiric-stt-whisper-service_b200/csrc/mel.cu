@@ -6,7 +6,16 @@
 //      the int16 -> f32 /32768 of transcribe_pcm16 (stt_engine.cpp:117-125) is folded into the load.
 //   2. mel_finalize_*       : clamp to max-8, (x+4)/4, and the layout change to what the conv stem
 //      consumes (time-major bf16 with zero pad rows).
-// HBM-bound by design (1.92 / 2.50 MB per 30 s window); v1 evaluates the DFT directly.
+// HBM-bound by bytes (1.92 / 2.50 MB per 30 s window). Generation 1 evaluated the 400-point DFT
+// directly (201 bins x 400 samples per frame: 482 MFMA per window, 66 us per window, 0.6 % of HBM).
+// Generation 2 factors it as 400 = 16 x 25 (Cooley-Tukey, n = 25 n1 + n2, k = k1 + 16 k2):
+//   stage A: 25 real 16-point DFTs over n1 (only k1 = 0..8 computed, the rest by conjugate symmetry),
+//            times the twiddle W400^(n2 k1);
+//   stage B: for each of the 201 wanted bins a 25-point DFT over n2;
+// 5.9 x fewer multiply-adds, all of it out of shared memory, f32 like upstream's own FFT. The mel
+// filterbank walks only the groups of four bins where the triangle of that filter has weight
+// (Model::filter_span): the partial sums are formed in upstream's order (four f32 products, then a
+// double add), and a group of zero weights adds exactly 0.0, so this is bit-identical to the dense loop.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -20,10 +29,14 @@ namespace {
 
 constexpr int FR = 8;        // frames per CTA
 constexpr int PW_LD = 209;   // power row stride (bank-conflict free for 8 frames)
+constexpr int N1 = 16, N2 = 25;
+constexpr int ZS_K1 = N2 * FR * 2 + 4;  // floats per k1 row of the stage-A output (+4: conflict-free LDS.128)
 
 struct MelTables {
-  float2* tw = nullptr;   // (cos, sin)(2*pi*i/400)
-  float* hann = nullptr;  // periodic Hann
+  float2* tw400 = nullptr;  // (cos, sin)(2*pi*i/400)
+  float2* tw16 = nullptr;   // (cos, sin)(2*pi*i/16)
+  float2* tw25 = nullptr;   // (cos, sin)(2*pi*i/25)
+  float* hann = nullptr;    // periodic Hann
 };
 MelTables g_tables[16];
 std::mutex g_tables_mu;
@@ -33,17 +46,23 @@ int get_tables(MelTables* out) {
   SW_CUDA_CHECK(cudaGetDevice(&dev));
   SW_CHECK(dev < 16, "device ordinal %d too large", dev);
   std::lock_guard<std::mutex> lk(g_tables_mu);
-  if (!g_tables[dev].tw) {
-    std::vector<float2> tw(MEL_N_FFT);
+  if (!g_tables[dev].tw400) {
+    auto upload_tw = [](int n, float2** dst) -> int {
+      std::vector<float2> tw(n);
+      for (int i = 0; i < n; ++i) {
+        const double th = (2.0 * M_PI * i) / n;
+        tw[i] = make_float2((float)cos(th), (float)sin(th));
+      }
+      SW_CUDA_CHECK(cudaMalloc(dst, sizeof(float2) * n));
+      SW_CUDA_CHECK(cudaMemcpy(*dst, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+      return 0;
+    };
+    if (upload_tw(MEL_N_FFT, &g_tables[dev].tw400) || upload_tw(N1, &g_tables[dev].tw16) ||
+        upload_tw(N2, &g_tables[dev].tw25))
+      return -1;
     std::vector<float> hann(MEL_N_FFT);
-    for (int i = 0; i < MEL_N_FFT; ++i) {
-      const double th = (2.0 * M_PI * i) / MEL_N_FFT;
-      tw[i] = make_float2(cosf(th), sinf(th));
-      hann[i] = 0.5 * (1.0 - cosf((2.0 * M_PI * i) / MEL_N_FFT));
-    }
-    SW_CUDA_CHECK(cudaMalloc(&g_tables[dev].tw, sizeof(float2) * MEL_N_FFT));
+    for (int i = 0; i < MEL_N_FFT; ++i) hann[i] = 0.5 * (1.0 - cosf((2.0 * M_PI * i) / MEL_N_FFT));
     SW_CUDA_CHECK(cudaMalloc(&g_tables[dev].hann, sizeof(float) * MEL_N_FFT));
-    SW_CUDA_CHECK(cudaMemcpy(g_tables[dev].tw, tw.data(), sizeof(float2) * MEL_N_FFT, cudaMemcpyHostToDevice));
     SW_CUDA_CHECK(cudaMemcpy(g_tables[dev].hann, hann.data(), sizeof(float) * MEL_N_FFT, cudaMemcpyHostToDevice));
   }
   *out = g_tables[dev];
@@ -66,12 +85,12 @@ __device__ __forceinline__ float load_sample(const void* pcm, int64_t off, int i
 
 template <bool F32>
 __global__ void __launch_bounds__(256)
-mel_log_power_kernel(const void* __restrict__ pcm, const MelUtt* __restrict__ utts,
-                     const float2* __restrict__ tw_g, const float* __restrict__ hann_g,
-                     const float* __restrict__ filters, int n_mel, float* __restrict__ log_out,
-                     unsigned* __restrict__ max_enc) {
+mel_log_power_kernel(const void* __restrict__ pcm, const MelUtt* __restrict__ utts, MelTables tabs,
+                     const float* __restrict__ filters, const int2* __restrict__ filter_span, int n_mel,
+                     float* __restrict__ log_out, unsigned* __restrict__ max_enc) {
   __shared__ __align__(16) float xs[MEL_N_FFT * FR];  // [n][frame], windowed
-  __shared__ float2 tw[MEL_N_FFT];
+  __shared__ __align__(16) float zs[N1 * ZS_K1];      // stage A: [k1][n2][frame](re, im), twiddled
+  __shared__ float2 tw16[N1], tw25[N2];
   __shared__ float pw[FR * PW_LD];
   __shared__ float red[8];
 
@@ -80,7 +99,8 @@ mel_log_power_kernel(const void* __restrict__ pcm, const MelUtt* __restrict__ ut
   if (f0 >= u.n_active) return;
   const int tid = threadIdx.x;
 
-  for (int i = tid; i < MEL_N_FFT; i += 256) tw[i] = tw_g[i];
+  if (tid < N1) tw16[tid] = tabs.tw16[tid];
+  if (tid >= 32 && tid < 32 + N2) tw25[tid - 32] = tabs.tw25[tid - 32];
   // framing: padded index p = f*160 + n; p < 200 reflects (pcm[200 - p]); else pcm[p - 200]; 0 past the end
   for (int i = tid; i < MEL_N_FFT * FR; i += 256) {
     const int n = i / FR, fr = i % FR;
@@ -88,19 +108,22 @@ mel_log_power_kernel(const void* __restrict__ pcm, const MelUtt* __restrict__ ut
     const int s = p < 200 ? 200 - p : p - 200;
     float v = 0.f;
     if (f0 + fr < u.n_active && s < u.n_samples) v = load_sample<F32>(pcm, u.pcm_off, s);
-    xs[i] = hann_g[n] * v;
+    xs[i] = tabs.hann[n] * v;
   }
   __syncthreads();
 
-  if (tid < MEL_N_BINS) {
+  // ---- stage A: thread (n2, k1 <= 8): Y[k1] = sum_n1 x[25 n1 + n2] W16^(n1 k1) for the 8 frames, then
+  // Z[k1] = Y[k1] W400^(n2 k1) and, for k1 = 1..7, Z[16 - k1] = conj(Y[k1]) W400^(n2 (16 - k1))
+  if (tid < N2 * 9) {
+    const int n2 = tid / 9, k1 = tid % 9;
     float re[FR], im[FR];
 #pragma unroll
     for (int f = 0; f < FR; ++f) re[f] = im[f] = 0.f;
-    int idx = 0;
     const float4* x4 = reinterpret_cast<const float4*>(xs);
-#pragma unroll 4
-    for (int n = 0; n < MEL_N_FFT; ++n) {
-      const float2 w = tw[idx];
+#pragma unroll
+    for (int n1 = 0; n1 < N1; ++n1) {
+      const float2 w = tw16[(n1 * k1) & (N1 - 1)];
+      const int n = N2 * n1 + n2;
       const float4 a = x4[2 * n], b = x4[2 * n + 1];
       re[0] += a.x * w.x; im[0] -= a.x * w.y;
       re[1] += a.y * w.x; im[1] -= a.y * w.y;
@@ -110,8 +133,50 @@ mel_log_power_kernel(const void* __restrict__ pcm, const MelUtt* __restrict__ ut
       re[5] += b.y * w.x; im[5] -= b.y * w.y;
       re[6] += b.z * w.x; im[6] -= b.z * w.y;
       re[7] += b.w * w.x; im[7] -= b.w * w.y;
-      idx += tid;
-      if (idx >= MEL_N_FFT) idx -= MEL_N_FFT;
+    }
+    {
+      const float2 t = __ldg(tabs.tw400 + n2 * k1);  // W400^(n2 k1) = cos - i sin
+      float* z = zs + k1 * ZS_K1 + n2 * (2 * FR);
+#pragma unroll
+      for (int f = 0; f < FR; f += 2)
+        *reinterpret_cast<float4*>(z + 2 * f) =
+            make_float4(re[f] * t.x + im[f] * t.y, im[f] * t.x - re[f] * t.y,
+                        re[f + 1] * t.x + im[f + 1] * t.y, im[f + 1] * t.x - re[f + 1] * t.y);
+    }
+    if (k1 >= 1 && k1 <= 7) {
+      const int kk = N1 - k1;
+      const float2 t = __ldg(tabs.tw400 + n2 * kk);
+      float* z = zs + kk * ZS_K1 + n2 * (2 * FR);
+#pragma unroll
+      for (int f = 0; f < FR; f += 2)  // conj(Y) = (re, -im)
+        *reinterpret_cast<float4*>(z + 2 * f) =
+            make_float4(re[f] * t.x - im[f] * t.y, -im[f] * t.x - re[f] * t.y,
+                        re[f + 1] * t.x - im[f + 1] * t.y, -im[f + 1] * t.x - re[f + 1] * t.y);
+    }
+  }
+  __syncthreads();
+
+  // ---- stage B: thread k = k1 + 16 k2: X[k] = sum_n2 Z[k1][n2] W25^(n2 k2); power spectrum
+  if (tid < MEL_N_BINS) {
+    const int k1 = tid & (N1 - 1), k2 = tid >> 4;
+    float re[FR], im[FR];
+#pragma unroll
+    for (int f = 0; f < FR; ++f) re[f] = im[f] = 0.f;
+    const float4* z4 = reinterpret_cast<const float4*>(zs + k1 * ZS_K1);
+    int idx = 0;
+#pragma unroll 5
+    for (int n2 = 0; n2 < N2; ++n2) {
+      const float2 w = tw25[idx];  // multiply by cos - i sin
+#pragma unroll
+      for (int q = 0; q < FR / 2; ++q) {
+        const float4 z = z4[n2 * (FR / 2) + q];  // (re, im) of frames 2q, 2q+1
+        re[2 * q] += z.x * w.x + z.y * w.y;
+        im[2 * q] += z.y * w.x - z.x * w.y;
+        re[2 * q + 1] += z.z * w.x + z.w * w.y;
+        im[2 * q + 1] += z.w * w.x - z.z * w.y;
+      }
+      idx += k2;
+      if (idx >= N2) idx -= N2;
     }
 #pragma unroll
     for (int f = 0; f < FR; ++f) pw[f * PW_LD + tid] = re[f] * re[f] + im[f] * im[f];
@@ -124,9 +189,11 @@ mel_log_power_kernel(const void* __restrict__ pcm, const MelUtt* __restrict__ ut
     if (f0 + fr >= u.n_active) continue;
     const float* fl = filters + (size_t)m * MEL_N_BINS;
     const float* p = pw + fr * PW_LD;
+    const int2 span = __ldg(filter_span + m);  // groups of four bins outside it hold zero weights: they add 0.0
     double sum = 0.0;
-    int k = 0;
-    for (; k < MEL_N_BINS - 3; k += 4) {
+    int k = span.x;
+    const int k_end = span.y < MEL_N_BINS - 3 ? span.y : MEL_N_BINS - 3;
+    for (; k < k_end; k += 4) {
       // upstream sums four float products in float, then adds to the double accumulator
       float g = __fmul_rn(p[k], __ldg(fl + k));
       g = __fadd_rn(g, __fmul_rn(p[k + 1], __ldg(fl + k + 1)));
@@ -134,7 +201,8 @@ mel_log_power_kernel(const void* __restrict__ pcm, const MelUtt* __restrict__ ut
       g = __fadd_rn(g, __fmul_rn(p[k + 3], __ldg(fl + k + 3)));
       sum += (double)g;
     }
-    for (; k < MEL_N_BINS; ++k) sum += (double)__fmul_rn(p[k], __ldg(fl + k));
+    if (span.y > MEL_N_BINS - 1)  // the scalar tail of upstream's loop: bin 200
+      for (k = MEL_N_BINS - 1; k < MEL_N_BINS; ++k) sum += (double)__fmul_rn(p[k], __ldg(fl + k));
     const float v = (float)log10(fmax(sum, 1e-10));
     log_out[u.log_off + (int64_t)m * u.n_active + f0 + fr] = v;
     lmax = fmaxf(lmax, v);
@@ -261,17 +329,17 @@ signal_energy_kernel(const void* __restrict__ pcm, const MelUtt* __restrict__ ut
 }  // namespace
 
 int mel_log_power(const void* pcm, int is_f32, const MelUtt* d_utts, int n_utts, int max_active,
-                  const float* d_filters, int n_mel, float* d_log, unsigned* d_max_enc,
-                  cudaStream_t stream) {
+                  const float* d_filters, const int2* d_filter_span, int n_mel, float* d_log,
+                  unsigned* d_max_enc, cudaStream_t stream) {
   if (n_utts <= 0 || max_active <= 0) return 0;
   SW_CHECK(n_mel <= 128, "n_mel %d > 128", n_mel);
   MelTables t;
   if (get_tables(&t)) return -1;
   dim3 grid((max_active + FR - 1) / FR, n_utts);
   if (is_f32)
-    mel_log_power_kernel<true><<<grid, 256, 0, stream>>>(pcm, d_utts, t.tw, t.hann, d_filters, n_mel, d_log, d_max_enc);
+    mel_log_power_kernel<true><<<grid, 256, 0, stream>>>(pcm, d_utts, t, d_filters, d_filter_span, n_mel, d_log, d_max_enc);
   else
-    mel_log_power_kernel<false><<<grid, 256, 0, stream>>>(pcm, d_utts, t.tw, t.hann, d_filters, n_mel, d_log, d_max_enc);
+    mel_log_power_kernel<false><<<grid, 256, 0, stream>>>(pcm, d_utts, t, d_filters, d_filter_span, n_mel, d_log, d_max_enc);
   SW_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

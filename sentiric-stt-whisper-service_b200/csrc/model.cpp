@@ -277,6 +277,22 @@ int load_impl(Model* m, const char* path) {
 
   ALLOC(m->filters, float, nm * 201);
   SW_CUDA_CHECK(cudaMemcpy(m->filters, filters.data(), filters.size() * 4, cudaMemcpyHostToDevice));
+  {  // the triangles are a few bins wide: the front end only walks the groups of four bins that hold a weight
+    std::vector<int2> span(nm);
+    for (size_t i = 0; i < nm; ++i) {
+      int lo = 201, hi = 0;
+      for (int k = 0; k < 201; ++k)
+        if (filters[i * 201 + k] != 0.0f) {
+          lo = std::min(lo, k);
+          hi = std::max(hi, k + 1);
+        }
+      if (lo >= hi) lo = hi = 0;
+      span[i].x = lo / 4 * 4;
+      span[i].y = hi;
+    }
+    ALLOC(m->filter_span, int2, nm);
+    SW_CUDA_CHECK(cudaMemcpy(m->filter_span, span.data(), span.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  }
   // conv weights: [d_out][c_in][3] -> [d_out][3][c_in]
   auto conv = [&](const std::string& name, int64_t cin, __nv_bfloat16*& dst) -> int {
     std::vector<float> w, r((size_t)d * 3 * cin);

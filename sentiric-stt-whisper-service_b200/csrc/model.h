@@ -49,6 +49,7 @@ struct Model {
   Vocab vocab;
   // device
   float* filters = nullptr;                 // [n_mel][201]
+  int2* filter_span = nullptr;              // [n_mel] first / one-past-last bin (multiples of 4) with a non-zero weight
   __nv_bfloat16* conv1_w = nullptr;         // [d][3][n_mel]  (K-major for the implicit GEMM)
   __nv_bfloat16* conv2_w = nullptr;         // [d][3][d]
   float *conv1_b = nullptr, *conv2_b = nullptr;

@@ -403,7 +403,7 @@ struct Run {
       std::fill(init.begin(), init.end(), ~b);  // ordered encoding of a negative float = complement
     }
     SW_CUDA_CHECK(cudaMemcpyAsync(e->d_max_enc.p, init.data(), n * sizeof(unsigned), cudaMemcpyHostToDevice, st));
-    if (mel_log_power(e->d_pcm.p, is_f32, e->d_utts.p, n, max_active, m.filters, n_mel, e->d_log.p,
+    if (mel_log_power(e->d_pcm.p, is_f32, e->d_utts.p, n, max_active, m.filters, m.filter_span, n_mel, e->d_log.p,
                       e->d_max_enc.p, st))
       return -1;
     e->times.n_launches++;

@@ -293,6 +293,35 @@ def main():
             encoder_tflops=enc_tf, encoder_frac_of_sustained_peak=enc_tf / pk["tf_sust"],
             decode_gbs=dec_gbs, decode_frac_of_hbm=dec_gbs / pk["hbm"]))
 
+    # ---- prosody row: every window cut into six 5 s segments, through the C ABI
+    # with host int16 buffers (upload inside the timed region), next to the reference's own host code
+    if rank == 0:
+        segs = [(k * 80000, (k + 1) * 80000) for k in range(6)]
+        eng.prosody_segments(host_np[0], segs)
+        t0 = time.perf_counter()
+        for i in range(W):
+            eng.prosody_segments(host_np[i], segs)
+        dtp = time.perf_counter() - t0
+        line["stages"]["prosody"] = dict(
+            gpu_audio_s_per_s=30.0 * W / dtp, ms_per_window=1e3 * dtp / W, segments_per_window=6,
+            pcm_gbs=W * 480000 * 2 / dtp / 1e9,
+            note="sw_prosody_segments_pcm16 per 30 s window, host int16 in, upload + 2 kernels + read-back")
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import prosody as pro
+            impl = pro.reference()
+            kind = "reference" if impl is not None else "port"
+            impl = impl or pro.oracle()
+            f32 = synth_audio.to_f32(host_np[0])
+            t0 = time.perf_counter()
+            for a, b in segs:
+                impl.extract(f32[a:b])
+            dtc = time.perf_counter() - t0
+            line["stages"]["prosody"]["cpu_baseline"] = dict(
+                value=30.0 / dtc, unit="audio-sec/sec", cores=1, kind=kind,
+                sample="extract_prosody over the 6 segments of one window (%s)" %
+                       ("oracle/_ref: the reference's own prosody_extractor.cpp" if kind == "reference"
+                        else "oracle/prosody_oracle.cpp"))
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import ora
         cores = os.cpu_count() or 1

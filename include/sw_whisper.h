@@ -171,6 +171,35 @@ typedef struct sw_stats {
 SW_API void sw_ctx_set_kernel_timing(sw_ctx* ctx, int on);
 SW_API int sw_ctx_get_stats(sw_ctx* ctx, sw_stats* out, int reset);
 
+/* ---- per-segment prosody ----------------------- *
+ * replaces the extract_prosody call the reference makes for every segment
+ * (stt_engine.cpp:313-334 -> prosody_extractor.cpp:31-224): all segments of one
+ * utterance in two kernel launches; the record has AffectiveTags' fields
+ * (prosody_extractor.h:6-18). Segments shorter than 160 samples get the
+ * reference's neutral record ('?', neutral, zeros). Results are bit-identical
+ * to the reference's host code (tests/test_prosody.py). */
+typedef struct sw_prosody_opts {   /* ProsodyOptions, prosody_extractor.h:20-26 */
+  float lpf_alpha, gender_threshold, min_pitch, max_pitch;
+} sw_prosody_opts;
+enum { SW_EMOTION_NEUTRAL = 0, SW_EMOTION_EXCITED = 1, SW_EMOTION_SAD = 2, SW_EMOTION_ANGRY = 3 };
+typedef struct sw_prosody {
+  char gender;                     /* 'M', 'F' or '?' (gender_proxy) */
+  int emotion;                     /* SW_EMOTION_* (emotion_proxy) */
+  float arousal, valence, pitch_mean, pitch_std, energy_mean, energy_std, spectral_centroid,
+      zero_crossing_rate;
+  float speaker_vec[8];
+} sw_prosody;
+SW_API sw_prosody_opts sw_prosody_default_opts(void);
+/* pcm: the utterance (host or device memory); segment i covers samples
+ * [seg_begin[i], seg_end[i]) - the caller does the centisecond -> sample
+ * conversion of stt_engine.cpp:313-320. out[n_segs]. */
+SW_API int sw_prosody_segments_f32(sw_ctx* ctx, const float* pcm, int64_t n_samples, int sample_rate,
+                                   const int64_t* seg_begin, const int64_t* seg_end, int n_segs,
+                                   const sw_prosody_opts* opts, sw_prosody* out);
+SW_API int sw_prosody_segments_pcm16(sw_ctx* ctx, const int16_t* pcm, int64_t n_samples, int sample_rate,
+                                     const int64_t* seg_begin, const int64_t* seg_end, int n_segs,
+                                     const sw_prosody_opts* opts, sw_prosody* out);
+
 /* ---- stage-level hooks (parity tests and roofline measurement) --------- *
  * Host pointers in, host pointers out, synchronous. */
 /* log-mel of one utterance (whisper.cpp log_mel_spectrogram): out is

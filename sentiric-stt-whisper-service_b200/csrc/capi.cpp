@@ -86,6 +86,7 @@ void sw_ctx_destroy(sw_ctx* ctx) {
   if (ctx->e) {
     cudaSetDevice(ctx->e->device);
     cudaDeviceSynchronize();
+    sw::prosody_state_free(ctx->prosody);
     for (Engine* l : ctx->lanes) delete l;
     delete ctx->e;
   }

@@ -111,6 +111,28 @@ int skinny_split_for(int N, int K);
 int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, const float* bias, int gelu,
                 bf16* out, int ldo, float* partial, int split, cudaStream_t stream);
 
+// ------------------------------------------------------------------ prosody (prosody.cu)
+// per-segment DSP of prosody_extractor.cpp:31-224 for all segments of an utterance
+struct ProsodySeg {     // one segment: samples [begin, begin + n_frames * shift) are analysed
+  int64_t begin;        // first sample in the PCM buffer
+  int n_frames;         // complete 10 ms frames
+  int frame_off;        // offset of its frames in the frame buffer
+};
+struct ProsodyFrame {   // per 10 ms frame
+  float rms;            // sqrt(mean x^2)
+  int zc;               // sign changes of the low-passed frame
+  int cycles;           // hysteresis cycle count of the low-passed frame
+  float sc;             // sum(|dx| k) / sum(|dx|)
+};
+struct ProsodyRaw {     // per segment, before the heuristics (which stay on the host: capi.cpp)
+  float energy_mean, energy_std, zcr_mean, sc_mean, pitch_median, pitch_std;
+  int peaks, n_frames, n_f0, pad;
+};
+int prosody_frames(const void* d_pcm, int is_f32, const ProsodySeg* d_segs, int n_segs, int max_frames, int shift,
+                   int warm, float alpha, ProsodyFrame* d_frames, cudaStream_t stream);
+int prosody_reduce(const ProsodySeg* d_segs, const ProsodyFrame* d_frames, int n_segs, int shift, int sample_rate,
+                   float min_pitch, float max_pitch, ProsodyRaw* d_out, cudaStream_t stream);
+
 // logit rules + log-softmax + pick (whisper_process_logits + whisper_sample_token)
 struct LogitRow {        // per-row rule state, built by the host sequencer
   int is_initial;        // no token sampled yet in this window

@@ -279,7 +279,7 @@ int load_impl(Model* m, const char* path) {
   SW_CUDA_CHECK(cudaMemcpy(m->filters, filters.data(), filters.size() * 4, cudaMemcpyHostToDevice));
   {  // the triangles are a few bins wide: the front end only walks the groups of four bins that hold a weight
     std::vector<int2> span(nm);
-    for (size_t i = 0; i < nm; ++i) {
+    for (size_t i = 0; i < (size_t)nm; ++i) {
       int lo = 201, hi = 0;
       for (int k = 0; k < 201; ++k)
         if (filters[i * 201 + k] != 0.0f) {

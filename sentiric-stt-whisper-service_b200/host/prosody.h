@@ -1,9 +1,9 @@
 // Affective / prosody tags attached to every segment (reference:
-// /root/reference/src/prosody_extractor.h). The DSP itself (prosody_extractor.cpp:31-224) is a
-// host-side O(n) pass outside the Whisper hot path: SURVEY.md §8(f) rank 3 ("next"). Until it is
-// rebuilt as a batched GPU kernel the engine calls a pluggable function; the built-in default
-// returns exactly what the reference returns for a segment too short to analyse
-// (prosody_extractor.cpp:35-47), so every field is present and well-formed.
+// /root/reference/src/prosody_extractor.h). The DSP itself (prosody_extractor.cpp:31-224, SURVEY.md
+// §8(f) rank 3) runs on the GPU for all segments of an utterance at once (csrc/prosody.cu behind
+// sw_prosody_segments_*, bit-identical to the reference's host code); SttEngine::set_prosody_fn can
+// replace it with a host function. neutral_prosody is what the reference returns for a segment too
+// short to analyse (prosody_extractor.cpp:35-47).
 #pragma once
 #include <cstddef>
 #include <functional>

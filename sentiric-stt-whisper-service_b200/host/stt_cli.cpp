@@ -59,9 +59,13 @@ int main(int argc, char** argv) {
              engine.batches_run());
       for (size_t k = 0; k < out[i].size(); ++k) {
         const TranscriptionResult& r = out[i][k];
-        printf("%s{\"t0\": %lld, \"t1\": %lld, \"prob\": %.6f, \"language\": \"%s\", \"speaker\": \"%s\", \"text\": \"%s\", \"tokens\": [",
+        printf("%s{\"t0\": %lld, \"t1\": %lld, \"prob\": %.6f, \"language\": \"%s\", \"speaker\": \"%s\", \"text\": \"%s\", ",
                k ? ", " : "", (long long)r.t0, (long long)r.t1, r.prob, r.language.c_str(), r.speaker_id.c_str(),
                json_escape(r.text).c_str());
+        printf("\"gender\": \"%s\", \"emotion\": \"%s\", \"prosody\": [%.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g], \"tokens\": [",
+               r.gender_proxy.c_str(), r.emotion_proxy.c_str(), r.affective.arousal, r.affective.valence, r.affective.pitch_mean,
+               r.affective.pitch_std, r.affective.energy_mean, r.affective.energy_std, r.affective.spectral_centroid,
+               r.affective.zero_crossing_rate);
         for (size_t j = 0; j < r.tokens.size(); ++j)
           printf("%s[\"%s\", %.6f, %lld, %lld]", j ? ", " : "", json_escape(r.tokens[j].text).c_str(), r.tokens[j].p,
                  (long long)r.tokens[j].t0, (long long)r.tokens[j].t1);

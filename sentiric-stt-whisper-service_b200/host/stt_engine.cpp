@@ -257,8 +257,16 @@ std::vector<TranscriptionResult> SttEngine::run_request(const float* pcm, size_t
   const float kMinAvgTokenProb = 0.40f;  // :264
   const int eot = sw_token_eot(ctx_);
   const int n_segments = sw_result_n_segments(req.result);  // :261
-  // prosody works on float samples: convert lazily, only the slices that are analysed
-  std::vector<float> slice;
+  // Pass 1 (:261-311): filters; the kept segments and their PCM slices (:313-320).
+  struct Kept {
+    std::string text;
+    int64_t t0, t1, s0, s1;
+    bool turn;
+    std::vector<TokenData> tokens;
+    int valid;
+    float avg_prob;
+  };
+  std::vector<Kept> kept;
   for (int i = 0; i < n_segments; ++i) {
     const char* text_c = sw_result_segment_text(req.result, i);
     const std::string text = text_c ? text_c : "";
@@ -281,31 +289,72 @@ std::vector<TranscriptionResult> SttEngine::run_request(const float* pcm, size_t
     const float avg_prob = valid > 0 ? static_cast<float>(total_prob / valid) : 0.0f;
     if (avg_prob < kMinAvgTokenProb && valid > 0) continue;  // :300-311
 
-    // :313-334 - slice the PCM of the segment for prosody + speaker id
     int64_t s0 = static_cast<int64_t>((static_cast<double>(t0) / 100.0) * 16000.0);
     int64_t s1 = static_cast<int64_t>((static_cast<double>(t1) / 100.0) * 16000.0);
     s0 = std::max<int64_t>(0, std::min<int64_t>(s0, (int64_t)pcm_size));
     s1 = std::max<int64_t>(s0, std::min<int64_t>(s1, (int64_t)pcm_size));
-    const size_t seg = static_cast<size_t>(s1 - s0);
-    AffectiveTags pros;
-    std::string spk = "?";
-    if (seg < 160) {
-      pros = prosody_fn_(nullptr, 0, 16000, options.prosody_opts);
-    } else {
+    kept.push_back({text, t0, t1, s0, s1, turn, std::move(tokens), valid, avg_prob});
+  }
+
+  // Pass 2 (:322-334): prosody of every kept segment. Default: all segments of the utterance in one
+  // batched GPU call (sw_prosody_segments_*: bit-identical to the reference's extract_prosody); a
+  // caller-supplied ProsodyFn (set_prosody_fn) is evaluated per segment on the host instead.
+  std::vector<AffectiveTags> tags(kept.size());
+  if (!prosody_fn_) {
+    std::vector<int64_t> b(kept.size()), e(kept.size());
+    for (size_t k = 0; k < kept.size(); ++k) b[k] = kept[k].s0, e[k] = kept[k].s1;
+    std::vector<sw_prosody> out(kept.size());
+    sw_prosody_opts po;
+    po.lpf_alpha = options.prosody_opts.lpf_alpha;
+    po.gender_threshold = options.prosody_opts.gender_threshold;
+    po.min_pitch = options.prosody_opts.min_pitch;
+    po.max_pitch = options.prosody_opts.max_pitch;
+    const int rc = kept.empty() ? 0
+                   : pcm ? sw_prosody_segments_f32(ctx_, pcm, (int64_t)pcm_size, 16000, b.data(), e.data(),
+                                                   (int)kept.size(), &po, out.data())
+                         : sw_prosody_segments_pcm16(ctx_, pcm16, (int64_t)pcm_size, 16000, b.data(), e.data(),
+                                                     (int)kept.size(), &po, out.data());
+    if (rc != 0) fprintf(stderr, "[stt_engine] prosody failed: %s\n", sw_last_error());
+    static const char* kEmotion[] = {"neutral", "excited", "sad", "angry"};
+    for (size_t k = 0; k < kept.size(); ++k) {
+      AffectiveTags& t = tags[k];
+      if (rc != 0) {
+        t = neutral_prosody(nullptr, 0, 16000, options.prosody_opts);
+        continue;
+      }
+      const sw_prosody& p = out[k];
+      t.gender_proxy = std::string(1, p.gender);
+      t.emotion_proxy = kEmotion[p.emotion & 3];
+      t.arousal = p.arousal; t.valence = p.valence; t.pitch_mean = p.pitch_mean; t.pitch_std = p.pitch_std;
+      t.energy_mean = p.energy_mean; t.energy_std = p.energy_std; t.spectral_centroid = p.spectral_centroid;
+      t.zero_crossing_rate = p.zero_crossing_rate;
+      t.speaker_vec.assign(p.speaker_vec, p.speaker_vec + 8);
+    }
+  } else {
+    std::vector<float> slice;
+    for (size_t k = 0; k < kept.size(); ++k) {
+      const size_t seg = static_cast<size_t>(kept[k].s1 - kept[k].s0);
+      if (seg < 160) {
+        tags[k] = prosody_fn_(nullptr, 0, 16000, options.prosody_opts);
+        continue;
+      }
       const float* p = nullptr;
       if (pcm) {
-        p = pcm + s0;
-      } else {
+        p = pcm + kept[k].s0;
+      } else {  // prosody works on float samples: convert only the slices that are analysed
         slice.resize(seg);
-        for (size_t k = 0; k < seg; ++k) slice[k] = static_cast<float>(pcm16[s0 + k]) / 32768.0f;
+        for (size_t q = 0; q < seg; ++q) slice[q] = static_cast<float>(pcm16[kept[k].s0 + q]) / 32768.0f;
         p = slice.data();
       }
-      pros = prosody_fn_(p, seg, 16000, options.prosody_opts);
-      bool any = false;
-      for (float v : pros.speaker_vec) any = any || v != 0.0f;
-      if (!pros.speaker_vec.empty() && any) spk = clusterer.assign_or_add(pros.speaker_vec);
+      tags[k] = prosody_fn_(p, seg, 16000, options.prosody_opts);
     }
-    results.push_back({text, req.language, avg_prob, t0, t1, turn, tokens, valid, pros.gender_proxy,
+  }
+  for (size_t k = 0; k < kept.size(); ++k) {
+    Kept& s = kept[k];
+    std::string spk = "?";  // :323, :330-332: segments of >= 160 samples are clustered
+    if (s.s1 - s.s0 >= 160 && !tags[k].speaker_vec.empty()) spk = clusterer.assign_or_add(tags[k].speaker_vec);
+    const AffectiveTags& pros = tags[k];
+    results.push_back({s.text, req.language, s.avg_prob, s.t0, s.t1, s.turn, s.tokens, s.valid, pros.gender_proxy,
                        pros.emotion_proxy, pros.arousal, pros.valence, pros, spk});  // :336-339
   }
   return results;

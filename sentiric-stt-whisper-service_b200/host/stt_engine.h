@@ -97,7 +97,7 @@ class SttEngine {
 
   Settings settings_;
   sw_ctx* ctx_ = nullptr;
-  ProsodyFn prosody_fn_ = neutral_prosody;
+  ProsodyFn prosody_fn_;  // empty: the batched GPU path (sw_prosody_segments_*)
 
   // admission: at most parallel_requests requests in the engine (the reference's whisper_state pool)
   std::mutex pool_mutex_;

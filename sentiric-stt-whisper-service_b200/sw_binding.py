@@ -58,6 +58,22 @@ class Stats(C.Structure):
                 ("n_xattn", C.c_long), ("xattn_bytes", C.c_double), ("n_lanes", C.c_long)]
 
 
+class ProsodyOpts(C.Structure):
+    _fields_ = [("lpf_alpha", C.c_float), ("gender_threshold", C.c_float), ("min_pitch", C.c_float),
+                ("max_pitch", C.c_float)]
+
+
+class Prosody(C.Structure):
+    _fields_ = [("gender", C.c_char), ("emotion", C.c_int), ("arousal", C.c_float), ("valence", C.c_float),
+                ("pitch_mean", C.c_float), ("pitch_std", C.c_float), ("energy_mean", C.c_float),
+                ("energy_std", C.c_float), ("spectral_centroid", C.c_float), ("zero_crossing_rate", C.c_float),
+                ("speaker_vec", C.c_float * 8)]
+
+
+EMOTIONS = ["neutral", "excited", "sad", "angry"]
+PROSODY_FLOATS = ["arousal", "valence", "pitch_mean", "pitch_std", "energy_mean", "energy_std",
+                  "spectral_centroid", "zero_crossing_rate"]
+
 EXPORTS = [
     "sw_last_error", "sw_version", "sw_device_count", "sw_log_set", "sw_ctx_default_params",
     "sw_ctx_create", "sw_ctx_destroy", "sw_ctx_model_info", "sw_token_to_str", "sw_token_eot",
@@ -67,6 +83,7 @@ EXPORTS = [
     "sw_result_segment_speaker_turn_next", "sw_result_n_tokens", "sw_result_token_data",
     "sw_result_lang_id", "sw_result_n_decode_steps", "sw_result_n_windows", "sw_result_free",
     "sw_ctx_get_stats", "sw_ctx_set_kernel_timing", "sw_mel_pcm16", "sw_mel_f32", "sw_encode", "sw_decode_logits",
+    "sw_prosody_default_opts", "sw_prosody_segments_f32", "sw_prosody_segments_pcm16",
     "sw_dev_gemm_bf16", "sw_dev_skinny_gemm", "sw_dev_skinny_split", "sw_dev_layer_norm"]
 
 _lib = None
@@ -256,6 +273,35 @@ class Engine:
         if self.L.sw_decode_logits(self.h, t.ctypes.data_as(C.POINTER(C.c_int32)), n, k, _fp(out)):
             raise RuntimeError(last_error())
         return out
+
+    def prosody_segments(self, pcm, segments, sample_rate=16000, **opts):
+        """pcm: float32 or int16 samples of one utterance; segments: [(begin, end)] in samples."""
+        a = np.ascontiguousarray(pcm)
+        assert a.dtype in (np.float32, np.int16)
+        n = len(segments)
+        b = (C.c_int64 * n)(*[int(s[0]) for s in segments])
+        e = (C.c_int64 * n)(*[int(s[1]) for s in segments])
+        self.L.sw_prosody_default_opts.restype = ProsodyOpts
+        o = self.L.sw_prosody_default_opts()
+        for k, v in opts.items():
+            setattr(o, k, v)
+        out = (Prosody * n)()
+        if a.dtype == np.float32:
+            fn, ptr = self.L.sw_prosody_segments_f32, a.ctypes.data_as(C.POINTER(C.c_float))
+        else:
+            fn, ptr = self.L.sw_prosody_segments_pcm16, a.ctypes.data_as(C.POINTER(C.c_int16))
+        fn.argtypes = [C.c_void_p, type(ptr), C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                       C.c_int, C.POINTER(ProsodyOpts), C.POINTER(Prosody)]
+        if fn(self.h, ptr, len(a), sample_rate, b, e, n, C.byref(o), out):
+            raise RuntimeError(last_error())
+        res = []
+        for p in out:
+            d = dict(gender=p.gender.decode(), emotion=EMOTIONS[p.emotion],
+                     speaker_vec=[float(x) for x in p.speaker_vec])
+            for f in PROSODY_FLOATS:
+                d[f] = float(getattr(p, f))
+            res.append(d)
+        return res
 
     def set_kernel_timing(self, on):
         self.L.sw_ctx_set_kernel_timing(self.h, int(on))

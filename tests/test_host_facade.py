@@ -65,4 +65,22 @@ def test_facade_matches_c_abi_and_batches_concurrent_callers(swb, tmp_path):
             assert len(gt) == len(wt)
         assert o["token_count"] == sum(len(s[2]) for s in segs)
         assert all(s["language"] == "en" for s in o["segments"])
+    # prosody + speaker ids of every returned segment (stt_engine.cpp:313-334): the facade's batched GPU
+    # call against the CPU oracle of prosody_extractor.cpp / speaker_cluster.cpp on the same PCM slices
+    from oracle import prosody
+    po = prosody.oracle()
+    f = synth_audio.to_f32(clip)
+    vecs = []
+    for s in outs[0]["segments"]:
+        a = max(0, min(int(s["t0"] / 100.0 * 16000.0), len(f)))
+        b = max(a, min(int(s["t1"] / 100.0 * 16000.0), len(f)))
+        want = po.extract(f[a:b]) if b - a >= 160 else po.extract(f[:0])
+        assert (s["gender"], s["emotion"]) == (want["gender"], want["emotion"])
+        got = np.array(s["prosody"], np.float32)
+        assert np.array_equal(got, np.array([want[k] for k in prosody.FLOAT_FIELDS], np.float32)), (s, want)
+        if b - a >= 160:
+            vecs.append(want["speaker_vec"])
+    ids = po.cluster(np.array(vecs, np.float32), 0.88) if vecs else []
+    got_ids = [s["speaker"] for s in outs[0]["segments"] if s["speaker"] != "?"]
+    assert got_ids == ["spk_%d" % k for k in ids]
     eng.close()

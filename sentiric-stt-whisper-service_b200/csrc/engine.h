@@ -79,6 +79,9 @@ struct Engine {
   DevBuf<int> d_win_utt, d_win_seek;
   DevBuf<float> d_energy;       // token-timestamp signal energy, same offsets as the PCM
   PinBuf<float> h_energy;
+  DevBuf<float> d_eblk;         // per 256-sample block min | max of the energy (two halves)
+  PinBuf<float> h_eblk;
+  size_t eblk_capacity = 0;
   size_t energy_capacity = 0;
   int utt_capacity = 0;
   // ---- encoder activations (max_batch windows)

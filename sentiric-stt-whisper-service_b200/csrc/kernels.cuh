@@ -22,6 +22,7 @@ struct MelUtt {            // one utterance, device-side descriptor
   int n_samples;           //
   int n_active;            // frames that see audio: min(n_eff/160 + 1, n_len)
   int n_len;               // frames incl. the 30 s zero pad
+  int blk_off;             // offset of its 256-sample blocks in the energy block-min / block-max arrays
   int64_t log_off;         // element offset of its [n_mel][n_active] log-mel in the log buffer
 };
 // log10 mel power of every active frame (before clamp/normalise) + per-utterance max.
@@ -43,8 +44,10 @@ int mel_finalize_full(const float* d_log, const MelUtt* d_utts, const unsigned* 
 int mel_f32_to_conv_input(const float* d_mel, int n_win, int n_mel, bf16* out, cudaStream_t stream);
 // get_signal_energy (token-level timestamps) for every utterance of the batch:
 // out[pcm_off + i] = sum_{|j|<=hw} |x[i+j]| / (2hw+1), summed in upstream's order (bit-exact)
+// blk_min / blk_max [blk_off + b]: min / max of out over samples [256 b, 256 b + 256) of the utterance, so
+// that the host's threshold scans (whisper_exp_compute_token_level_timestamps) can step over whole blocks
 int signal_energy(const void* pcm, int is_f32, const MelUtt* d_utts, int n_utts, int max_n, int hw,
-                  float* out, cudaStream_t stream);
+                  float* out, float* blk_min, float* blk_max, cudaStream_t stream);
 
 // ------------------------------------------------------------------ elementwise (elementwise.cu)
 // y = LN(x) * g + b over rows of d (eps 1e-5, f32 statistics). out_bf16/out_f32 may be null.
@@ -85,6 +88,7 @@ struct DecRow {    // one decoder row of a step
                             // the attention kernel needs no second dependent lookup
   int pad[2];
 };
+static_assert(sizeof(MelUtt) == 32, "MelUtt is uploaded as is");
 static_assert(sizeof(DecRow) == 80, "DecRow is uploaded as 20 ints");
 // pool layout: [page][layer][2][KV_PAGE][d]
 // pool[dst page] = pool[src page] for n pairs (src, dst); page_elems bf16 elements per page

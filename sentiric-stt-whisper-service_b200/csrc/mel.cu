@@ -307,8 +307,9 @@ mel_f32_to_conv_input_kernel(const float* __restrict__ mel, int n_mel, bf16* __r
 template <bool F32>
 __global__ void __launch_bounds__(256)
 signal_energy_kernel(const void* __restrict__ pcm, const MelUtt* __restrict__ utts, int hw,
-                     float* __restrict__ out) {
+                     float* __restrict__ out, float* __restrict__ blk_min, float* __restrict__ blk_max) {
   extern __shared__ float sh[];  // 256 + 2*hw, |x|
+  __shared__ float rmin[8], rmax[8];
   const MelUtt u = utts[blockIdx.y];
   const int n = u.n_samples;
   if ((int)blockIdx.x * 256 >= n) return;
@@ -319,11 +320,35 @@ signal_energy_kernel(const void* __restrict__ pcm, const MelUtt* __restrict__ ut
   }
   __syncthreads();
   const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= n) return;
-  float sum = 0.f;
-  for (int j = -hw; j <= hw; ++j)
-    if (i + j >= 0 && i + j < n) sum = __fadd_rn(sum, sh[threadIdx.x + hw + j]);
-  out[u.pcm_off + i] = sum / (float)(2 * hw + 1);
+  float v = 0.f;
+  if (i < n) {
+    float sum = 0.f;
+    for (int j = -hw; j <= hw; ++j)
+      if (i + j >= 0 && i + j < n) sum = __fadd_rn(sum, sh[threadIdx.x + hw + j]);
+    v = sum / (float)(2 * hw + 1);
+    out[u.pcm_off + i] = v;
+  }
+  // min / max of this block's valid samples
+  float lo = i < n ? v : INFINITY, hi = i < n ? v : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    rmin[threadIdx.x >> 5] = lo;
+    rmax[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      lo = fminf(lo, rmin[w]);
+      hi = fmaxf(hi, rmax[w]);
+    }
+    blk_min[u.blk_off + blockIdx.x] = lo;
+    blk_max[u.blk_off + blockIdx.x] = hi;
+  }
 }
 
 }  // namespace
@@ -371,14 +396,14 @@ int mel_f32_to_conv_input(const float* d_mel, int n_win, int n_mel, bf16* out, c
 }
 
 int signal_energy(const void* pcm, int is_f32, const MelUtt* d_utts, int n_utts, int max_n, int hw,
-                  float* out, cudaStream_t stream) {
+                  float* out, float* blk_min, float* blk_max, cudaStream_t stream) {
   if (n_utts <= 0 || max_n <= 0) return 0;
   dim3 grid((max_n + 255) / 256, n_utts);
   const size_t sh = (256 + 2 * hw) * sizeof(float);
   if (is_f32)
-    signal_energy_kernel<true><<<grid, 256, sh, stream>>>(pcm, d_utts, hw, out);
+    signal_energy_kernel<true><<<grid, 256, sh, stream>>>(pcm, d_utts, hw, out, blk_min, blk_max);
   else
-    signal_energy_kernel<false><<<grid, 256, sh, stream>>>(pcm, d_utts, hw, out);
+    signal_energy_kernel<false><<<grid, 256, sh, stream>>>(pcm, d_utts, hw, out, blk_min, blk_max);
   SW_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

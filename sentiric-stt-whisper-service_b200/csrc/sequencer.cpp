@@ -49,6 +49,8 @@ struct Utt {
   std::vector<int> prompt_past;
   std::mt19937 rng[8];
   const float* energy = nullptr;  // smoothed |x| (pinned host buffer of the engine)
+  const float* en_bmin = nullptr;  // min / max of every 256-sample block of it
+  const float* en_bmax = nullptr;
   int n_energy = 0;
   int64_t t_beg = 0, t_last = 0;
   int tid_last = 0;
@@ -231,8 +233,12 @@ void token_timestamps(const Model& m, Utt& u, sw_segment& seg) {
       tk[j].t1 = std::max(tk[j].t0, tk[j].t1);
     }
   }
-  // expand / contract on the smoothed signal energy
+  // expand / contract on the smoothed signal energy. The four threshold scans below are upstream's
+  // sample-by-sample while loops; with speech-like audio one of them can run over most of the utterance
+  // for every token (10 ms of host time per window). They step over a whole 256-sample block when the
+  // block's min (max) proves that every sample of it passes the loop condition: same result, exactly.
   const float* en = u.energy;
+  const float *bmin = u.en_bmin, *bmax = u.en_bmax;
   const int hw = SR / 8;
   for (int j = 0; j < n; ++j) {
     if (tk[j].id >= m.vocab.eot) continue;
@@ -245,12 +251,18 @@ void token_timestamps(const Model& m, Utt& u, sw_segment& seg) {
     {
       int k = s0;
       if (en[k] > thold && j > 0) {
-        while (k > 0 && en[k] > thold) k--;
+        while (k > 0 && en[k] > thold) {
+          if (bmin[k >> 8] > thold) k = (k >> 8) << 8;  // every sample down to the block start is above
+          if (k > 0) k--;
+        }
         tk[j].t0 = sample_to_ts(k);
         if (tk[j].t0 < tk[j - 1].t1) tk[j].t0 = tk[j - 1].t1;
         else s0 = k;
       } else {
-        while (en[k] < thold && k < s1) k++;
+        while (en[k] < thold && k < s1) {
+          if (bmax[k >> 8] < thold) k = std::min(s1, ((k >> 8) + 1) << 8);
+          else k++;
+        }
         s0 = k;
         tk[j].t0 = sample_to_ts(k);
       }
@@ -258,12 +270,18 @@ void token_timestamps(const Model& m, Utt& u, sw_segment& seg) {
     {
       int k = s1;
       if (en[k] > thold) {
-        while (k < n_samples - 1 && en[k] > thold) k++;
+        while (k < n_samples - 1 && en[k] > thold) {
+          if (bmin[k >> 8] > thold) k = std::min(n_samples - 1, (((k >> 8) + 1) << 8) - 1);
+          if (k < n_samples - 1) k++;
+        }
         tk[j].t1 = sample_to_ts(k);
         if (j < n - 1 && tk[j].t1 > tk[j + 1].t0) tk[j].t1 = tk[j + 1].t0;
         else s1 = k;
       } else {
-        while (en[k] < thold && k > s0) k--;
+        while (en[k] < thold && k > s0) {
+          if (bmax[k >> 8] < thold) k = std::max(s0, ((k >> 8) << 8) - 1);
+          else k--;
+        }
         s1 = k;
         tk[j].t1 = sample_to_ts(k);
       }
@@ -349,7 +367,7 @@ struct Run {
     const size_t es = is_f32 ? 4 : 2;
     std::vector<MelUtt> mu(n);
     int64_t pcm_off = 0, log_off = 0;
-    int max_active = 0;
+    int max_active = 0, blk_off = 0;
     utts.resize(n);
     for (int i = 0; i < n; ++i) {
       Utt& u = utts[i];
@@ -363,6 +381,8 @@ struct Run {
       mu[i].n_active = u.n_active;
       mu[i].n_len = u.n_len;
       mu[i].log_off = log_off;
+      mu[i].blk_off = blk_off;
+      blk_off += (u.n_samples + 255) / 256;
       pcm_off += ((int64_t)u.n_samples + 7) / 8 * 8;
       log_off += (int64_t)n_mel * u.n_active;
       max_active = std::max(max_active, u.n_active);
@@ -416,12 +436,23 @@ struct Run {
         e->energy_capacity = (size_t)pcm_off * 5 / 4 + 1024;
         if (e->d_energy.alloc(e->energy_capacity) || e->h_energy.alloc(e->energy_capacity)) return -1;
       }
-      if (signal_energy(e->d_pcm.p, is_f32, e->d_utts.p, n, max_n, 32, e->d_energy.p, st)) return -1;
+      if ((size_t)blk_off > e->eblk_capacity) {
+        e->d_eblk.release();
+        e->h_eblk.release();
+        e->eblk_capacity = (size_t)blk_off * 5 / 4 + 64;
+        if (e->d_eblk.alloc(2 * e->eblk_capacity) || e->h_eblk.alloc(2 * e->eblk_capacity)) return -1;
+      }
+      if (signal_energy(e->d_pcm.p, is_f32, e->d_utts.p, n, max_n, 32, e->d_energy.p, e->d_eblk.p,
+                        e->d_eblk.p + e->eblk_capacity, st))
+        return -1;
       e->times.n_launches++;
       SW_CUDA_CHECK(cudaMemcpyAsync(e->h_energy.p, e->d_energy.p, (size_t)pcm_off * 4, cudaMemcpyDeviceToHost, st));
-      e->times.d2h_bytes += (double)pcm_off * 4;
+      SW_CUDA_CHECK(cudaMemcpyAsync(e->h_eblk.p, e->d_eblk.p, 2 * e->eblk_capacity * 4, cudaMemcpyDeviceToHost, st));
+      e->times.d2h_bytes += (double)pcm_off * 4 + 2.0 * blk_off * 4;
       for (int i = 0; i < n; ++i) {
         utts[i].energy = e->h_energy.p + mu[i].pcm_off;
+        utts[i].en_bmin = e->h_eblk.p + mu[i].blk_off;
+        utts[i].en_bmax = e->h_eblk.p + e->eblk_capacity + mu[i].blk_off;
         utts[i].n_energy = n_samples[i];
       }
     }
@@ -1073,7 +1104,9 @@ struct Run {
     };
     auto collect = [&]() -> int {
       if (!pend.active) return 0;
+      const double tc0 = wall_ms();
       pend.th.join();
+      if (trace) fprintf(stderr, "[sw trace] waited %.1f ms for the host post-processing of %d windows\n", wall_ms() - tc0, (int)pend.wins.size());
       pend.active = false;
       SW_CHECK(!pend.failed, "out of host memory while building results");
       for (size_t i = 0; i < pend.wins.size(); ++i) {
@@ -1124,6 +1157,7 @@ struct Run {
                 (int)wins.size(), tw1 - tw0, tw2 - tw1, wall_ms() - tw2);
       start_finish(std::move(wins));
     }
+    if (trace) fprintf(stderr, "[sw trace] run of %d utterances: %.1f ms (wall)\n", n, wall_ms() - tf0);
     return 0;
   }
 };

@@ -155,76 +155,102 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
     for (int i = 0; i < DH; ++i) acc[i] = 0.f;
     uint8_t* prow = smem + SM_P + row * 128;
     float alpha_prev = 1.f;
+    // Every tcgen05.ld below is issued one chunk AHEAD of the arithmetic that consumes it (two register
+    // buffers, tcgen05.wait::ld right before the use): generation 2.0 of this kernel waited for each of its
+    // ten loads per tile (~250 cycles each, 2 500 of the ~5 000 cycles a warp spent per tile), which left
+    // the MUFU pipe - the real bound of a 64-wide head, 128 ex2 per row and tile - half idle.
     auto fold_o = [&](int j, float a) {  // acc = acc * a + O_j
       mbar_wait(&o_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      uint32_t ra[32], rb[32];
+      const uint32_t o_addr = tmem + lane_addr + 128 + (j & 1) * 64;
+      tmem_ld_32x32b_x32(o_addr, ra);
+      tmem_ld_32x32b_x32(o_addr + 32, rb);
+      tmem_ld_wait(ra);
+      tmem_ld_wait(rb);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem + lane_addr + 128 + (j & 1) * 64 + c * 32, r);
-        tmem_ld_wait();
+      for (int i = 0; i < 32; ++i) acc[i] = acc[i] * a + __uint_as_float(ra[i]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * a + __uint_as_float(r[i]);
-      }
+      for (int i = 0; i < 32; ++i) acc[32 + i] = acc[32 + i] * a + __uint_as_float(rb[i]);
       tc_fence_before();
+    };
+    const uint32_t s_addr = tmem + lane_addr;
+    auto chunk_max = [&](const uint32_t (&r)[32], int c, int valid, float& mx) {
+      if (c * 32 + 32 <= valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+    };
+    auto chunk_exp = [&](const uint32_t (&r)[32], int c, int valid, float mn, float& lsum) {
+      uint32_t pk[16];
+      if (c * 32 + 32 <= valid) {  // full chunk: no masking
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
+          const float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
+          lsum += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
+          float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
+          if (c * 32 + 2 * i >= valid) p0 = 0.f;
+          if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
+          lsum += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+      }
+      // 32 keys = 4 chunks of 16 B; chunk index within the 64-key atom: (c & 1) * 4 + q
+      uint8_t* atom = prow + (c >> 1) * TILE_BYTES;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const int ch = (c & 1) * 4 + qq;
+        *reinterpret_cast<uint4*>(atom + ((ch ^ (row & 7)) << 4)) =
+            make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+      }
     };
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = min(TK, T - j * TK);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      uint32_t ra[32], rb[32];
+      // ---- pass 1: row maximum of the 128 scores
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem + lane_addr + c * 32, r);
-        tmem_ld_wait();
-        if (c * 32 + 32 <= valid) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
-      }
+      tmem_ld_32x32b_x32(s_addr, ra);
+      tmem_ld_wait(ra);
+      tmem_ld_32x32b_x32(s_addr + 32, rb);
+      chunk_max(ra, 0, valid, mx);
+      tmem_ld_wait(rb);
+      tmem_ld_32x32b_x32(s_addr + 64, ra);
+      chunk_max(rb, 1, valid, mx);
+      tmem_ld_wait(ra);
+      tmem_ld_32x32b_x32(s_addr + 96, rb);
+      chunk_max(ra, 2, valid, mx);
+      tmem_ld_wait(rb);
+      tmem_ld_32x32b_x32(s_addr, ra);  // chunk 0 again, for pass 2
+      chunk_max(rb, 3, valid, mx);
       const float mn = fmaxf(m, mx * sc);
       const float alpha = fast_exp2(m - mn);
       m = mn;
+      // ---- pass 2: P = exp2(S * sc - m) -> bf16 -> shared memory (the A operand of P V)
       float lsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem + lane_addr + c * 32, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        if (c * 32 + 32 <= valid) {  // full chunk: no masking
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
-            const float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
-            lsum += p0 + p1;
-            pk[i] = pack_bf16x2(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
-            float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
-            if (c * 32 + 2 * i >= valid) p0 = 0.f;
-            if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
-            lsum += p0 + p1;
-            pk[i] = pack_bf16x2(p0, p1);
-          }
-        }
-        // 32 keys = 4 chunks of 16 B; chunk index within the 64-key atom: (c & 1) * 4 + q
-        uint8_t* atom = prow + (c >> 1) * TILE_BYTES;
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          const int ch = (c & 1) * 4 + qq;
-          *reinterpret_cast<uint4*>(atom + ((ch ^ (row & 7)) << 4)) =
-              make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
-        }
-      }
+      tmem_ld_wait(ra);
+      tmem_ld_32x32b_x32(s_addr + 32, rb);
+      chunk_exp(ra, 0, valid, mn, lsum);
+      tmem_ld_wait(rb);
+      tmem_ld_32x32b_x32(s_addr + 64, ra);
+      chunk_exp(rb, 1, valid, mn, lsum);
+      tmem_ld_wait(ra);
+      tmem_ld_32x32b_x32(s_addr + 96, rb);
+      chunk_exp(ra, 2, valid, mn, lsum);
+      tmem_ld_wait(rb);
+      chunk_exp(rb, 3, valid, mn, lsum);
       l = l * alpha + lsum;
       tc_fence_before();
       fence_proxy_async_smem();

@@ -242,6 +242,19 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// The same, naming the registers an earlier tcgen05.ld is filling: they are in/out operands of the wait, so
+// the compiler cannot schedule arithmetic on them ahead of it (needed once loads are issued a chunk ahead
+// of their use and other arithmetic sits between the load and its wait).
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :
+      : "memory");
+}
 
 // K-major, 128B-swizzled shared-memory operand descriptor (tile rows are 128 B
 // = 64 bf16 wide, written by TMA with CU_TENSOR_MAP_SWIZZLE_128B):

@@ -64,11 +64,22 @@ def model_path(size, script_len):
 def ensure_model(size, script_len):
     from tools import gen_model
     path = model_path(size, script_len)
-    if not os.path.exists(path):
+    if not (os.path.exists(path) and os.path.exists(path + ".json")):
         tmp = path + ".tmp%d" % os.getpid()
-        gen_model.generate(tmp, size, script_len=script_len)
+        info = gen_model.generate(tmp, size, script_len=script_len)
         os.replace(tmp, path)
+        json.dump(dict(script=[int(t) for t in info["script"]], beg=int(info["special"]["beg"])),
+                  open(path + ".json", "w"))
     return path
+
+
+def scripted_tokens(path):
+    """The transcript the seeded decoder is scripted to follow, as the engine reports it (a timestamp that
+    repeats the previous token closes a segment and is reported once): the bench checks every window
+    against it, so a fast step that decodes something else cannot pass unnoticed."""
+    info = json.load(open(path + ".json"))
+    sc, beg = info["script"], info["beg"]
+    return [t for i, t in enumerate(sc[:-1]) if not (i > 0 and t >= beg and sc[i - 1] == t)]
 
 
 class ClockSampler:
@@ -205,12 +216,23 @@ def main():
     host_ptrs = (ptr16 * W)(*[C.cast(host + i * n_s * 2, ptr16) for i in range(W)])
     dev_ptrs = (ptr16 * W)(*[C.cast(dev.data_ptr() + i * n_s * 2, ptr16) for i in range(W)])
 
-    def step(ptrs):
+    want_ids = scripted_tokens(path)
+    L.sw_result_token_data.restype = swb.TokenData
+    parity = dict(windows=0, token_identical_to_script=0)
+
+    def step(ptrs, check=False):
         res = eng.full_batch_ptrs(ptrs, lens, W, params)
         n_tok = 0
         for r in res:
+            ids = []
             for s in range(L.sw_result_n_segments(r)):
-                n_tok += L.sw_result_n_tokens(r, s)
+                nt = L.sw_result_n_tokens(r, s)
+                n_tok += nt
+                if check:
+                    ids += [L.sw_result_token_data(r, s, j).id for j in range(nt)]
+            if check:
+                parity["windows"] += 1
+                parity["token_identical_to_script"] += int(ids == want_ids)
             L.sw_result_free(r)
         return n_tok
 
@@ -228,8 +250,8 @@ def main():
             dt = float(t.item())
         return dt, n_tok
 
-    for _ in range(args.warmup):
-        step(dev_ptrs)
+    for i in range(args.warmup):
+        step(dev_ptrs, check=(i == 0))  # untimed: every window of the first warm-up pass is checked
     eng.stats(reset=True)
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -276,6 +298,8 @@ def main():
                  h2d_bytes_per_step=int(st_e2e["h2d_bytes"] / args.steps),
                  d2h_bytes_per_step=int(st_e2e["d2h_bytes"] / args.steps)),
         gpu_launches=int(st["n_launches"]),
+        parity_check=dict(parity, note="greedy token ids of every window of one pass vs the transcript the "
+                                       "seeded decoder is scripted to follow (tests compare with the CPU oracle)"),
         clocks=clk,
         roofline=dict(bound="hbm", kernel="cross_attention_kernel", achieved=xa_gbs, peak=pk["hbm"],
                       unit="GB/s", frac=xa_gbs / pk["hbm"], traffic=None,

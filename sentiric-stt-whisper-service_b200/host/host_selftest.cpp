@@ -2,11 +2,13 @@
 // model file validation, and the constructor's failure contract.
 #include <assert.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <filesystem>
 #include <fstream>
 
 #include "model_manager.h"
+#include "stream_session.h"
 #include "stt_engine.h"
 #include "text_filters.h"
 
@@ -57,6 +59,34 @@ int main(int argc, char** argv) {
     threw = std::string(ex.what()) == "Whisper model initialization failed";
   }
   assert(threw);
+  // grpc_server.cpp:129-305 streaming policy, with a fake engine that reports the buffer length
+  {
+    std::vector<size_t> passes;
+    StreamSession ss(
+        [&](const std::vector<int16_t>& b) {
+          passes.push_back(b.size());
+          TranscriptionResult r{};
+          r.text = "n=" + std::to_string(b.size());
+          return std::vector<TranscriptionResult>{r};
+        },
+        8000);
+    std::string wav(44 + 2 * 3000, '\0');
+    memcpy(&wav[0], "RIFF", 4);
+    memcpy(&wav[8], "WAVE", 4);
+    assert(ss.feed(wav).empty() && ss.buffered_samples() == 3000);   // header skipped, below the 0.5 s step
+    const std::string pcm(2 * 5000, '\1');
+    auto ev = ss.feed(pcm);                                          // 8000 samples: one partial over ALL of them
+    assert(ev.size() == 1 && !ev[0].is_final && ev[0].transcription == "n=8000 " && ss.buffered_samples() == 8000);
+    assert(ss.feed(std::string(2 * 100, '\1')).empty());            // 100 new samples: no pass
+    ev = ss.feed("");                                                // end of sentence: final, buffer reset
+    assert(ev.size() == 1 && ev[0].is_final && ev[0].transcription == "n=8100" && ss.buffered_samples() == 0);
+    assert(ss.feed("").empty());
+    for (int i = 0; i < 60; ++i) ev = ss.feed(std::string(2 * 8000, '\1'));  // 30 s without a pause
+    assert(ev.size() == 1 && !ev[0].is_final && ss.buffered_samples() == 480000);
+    ev = ss.feed(std::string(2 * 8000, '\1'));                      // past 30 s: partial + forced final, reset
+    assert(ev.size() == 2 && !ev[0].is_final && ev[1].is_final && ss.buffered_samples() == 0);
+    assert(passes.size() == 1 + 1 + 61);
+  }
   printf("HOST_SELFTEST_OK\n");
   return 0;
 }

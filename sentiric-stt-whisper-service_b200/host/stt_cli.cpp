@@ -9,6 +9,7 @@
 #include <fstream>
 #include <thread>
 
+#include "stream_session.h"
 #include "stt_engine.h"
 
 static std::string json_escape(const std::string& s) {
@@ -30,7 +31,7 @@ static std::string json_escape(const std::string& s) {
 
 int main(int argc, char** argv) {
   if (argc < 4) {
-    fprintf(stderr, "usage: %s <model_dir> <model_file> <pcm16.raw> [n_concurrent] [beam]\n", argv[0]);
+    fprintf(stderr, "usage: %s <model_dir> <model_file> <pcm16.raw> [n_concurrent] [beam] [stream]\n", argv[0]);
     return 2;
   }
   Settings s;
@@ -46,6 +47,45 @@ int main(int argc, char** argv) {
   std::vector<char> raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
   std::vector<int16_t> pcm(raw.size() / 2);
   memcpy(pcm.data(), raw.data(), pcm.size() * 2);
+  const bool stream_mode = argc > 6 && std::string(argv[6]) == "stream";
+  if (stream_mode) {
+    // n_conc concurrent streams (grpc_server.cpp:129-305 policy through StreamSession), each fed the clip in
+    // 0.5 s chunks and closed with an empty chunk: their re-transcriptions meet in the dispatcher
+    try {
+      SttEngine engine(s);
+      std::vector<std::string> finals(n_conc);
+      std::vector<int> partials(n_conc, 0), calls(n_conc, 0);
+      std::vector<std::thread> th;
+      for (int i = 0; i < n_conc; ++i)
+        th.emplace_back([&, i] {
+          StreamSession ss(
+              [&, i](const std::vector<int16_t>& b) {
+                ++calls[i];
+                return engine.transcribe_pcm16(b, 16000, RequestOptions());
+              },
+              (size_t)engine.get_settings().stream_buffer_samples);
+          const size_t step = 8000;
+          for (size_t off = 0; off < pcm.size(); off += step) {
+            const size_t n = std::min(step, pcm.size() - off);
+            for (auto& e : ss.feed(std::string(reinterpret_cast<const char*>(pcm.data() + off), n * 2)))
+              partials[i] += e.is_final ? 0 : 1;
+          }
+          for (auto& e : ss.feed(""))
+            if (e.is_final) finals[i] += e.transcription + "|";
+        });
+      for (auto& t : th) t.join();
+      int total_calls = 0;
+      for (int c : calls) total_calls += c;
+      printf("{\"streams\": %d, \"transcribe_calls\": %d, \"batches_run\": %ld, \"partials\": %d, \"finals\": [", n_conc,
+             total_calls, engine.batches_run(), partials[0]);
+      for (int i = 0; i < n_conc; ++i) printf("%s\"%s\"", i ? ", " : "", json_escape(finals[i]).c_str());
+      printf("]}\n");
+      return 0;
+    } catch (const std::exception& e) {
+      fprintf(stderr, "error: %s\n", e.what());
+      return 1;
+    }
+  }
   try {
     SttEngine engine(s);
     std::vector<std::vector<TranscriptionResult>> out(n_conc);

@@ -84,3 +84,27 @@ def test_facade_matches_c_abi_and_batches_concurrent_callers(swb, tmp_path):
     got_ids = [s["speaker"] for s in outs[0]["segments"] if s["speaker"] != "?"]
     assert got_ids == ["spk_%d" % k for k in ids]
     eng.close()
+
+
+@pytest.mark.gpu
+def test_concurrent_streams_share_device_passes(tmp_path):
+    """the streaming policy of grpc_server.cpp:129-305 (StreamSession) re-transcribes
+    the whole buffer of a stream every 0.5 s; the re-transcriptions of concurrent streams are batched by the
+    facade's dispatcher, and the final text of a stream equals the one-shot transcription of its audio."""
+    build_host()
+    path, info = model_file("tiny")
+    clip = synth_audio.utterance(3, 22, seconds=6.0)
+    raw = tmp_path / "clip.raw"
+    clip.tofile(raw)
+    cli = os.path.join(HOST, "build", "stt_cli")
+    args = [os.path.dirname(path), os.path.basename(path), str(raw)]
+    one = subprocess.run([cli] + args + ["1", "1"], capture_output=True, text=True, timeout=300)
+    assert one.returncode == 0, one.stdout + one.stderr
+    want = "|".join(s["text"] for s in json.loads(one.stdout.strip().splitlines()[0])["segments"]) + "|"
+    r = subprocess.run([cli] + args + ["6", "1", "stream"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    o = json.loads(r.stdout.strip().splitlines()[-1])
+    assert o["streams"] == 6 and o["transcribe_calls"] == 6 * 13  # 12 partial passes + the final one each
+    assert o["batches_run"] < o["transcribe_calls"] // 2           # concurrent streams shared device passes
+    assert o["partials"] >= 10
+    assert all(f == want for f in o["finals"]), (o["finals"], want)

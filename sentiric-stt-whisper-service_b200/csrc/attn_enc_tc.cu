@@ -11,6 +11,8 @@
 // Two CTAs share an SM (112 KB smem, 256 TMEM columns each): one CTA's softmax overlaps the other's
 // MMAs. Replaces ggml's flash_attn_ext in whisper_encode_internal; generation 1
 // (attn_enc.cu, mma.sync) reached 298 TFLOP/s and was 35 % of the encoder time.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
@@ -22,8 +24,9 @@ constexpr int TQ = 128, TK = 128, DH = 64;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128 rows][64 bf16] swizzled tile
 constexpr int SM_Q = 0, SM_K = TILE_BYTES, SM_V = 3 * TILE_BYTES, SM_P = 5 * TILE_BYTES;
 constexpr int SM_BARS = 7 * TILE_BYTES;
-constexpr int ATT_SMEM = SM_BARS + 128;
-constexpr int ATT_THREADS = 192;
+constexpr int SM_XCH = SM_BARS + 128;  // [2 halves][128 rows] bf16: the row maxima the two threads of a row exchange
+constexpr int ATT_SMEM = SM_XCH + 512;  // two CTAs per SM: 2 x (ATT_SMEM + 1 KB reserved) <= 228 KB
+constexpr int ATT_THREADS = 320;       // warp 0: TMA, warp 1: TMEM + MMA issue, warps 2-9: softmax
 constexpr int TMEM_COLS = 256;  // S: columns [0,128), O double-buffered: [128,192) and [192,256)
 
 // MN-major 128B-swizzled operand (the V tile: rows = keys (K), 64 dims (MN) contiguous per row):
@@ -45,7 +48,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
-encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict__ out, int T, int d) {
+encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict__ out, int T, int d,
+                            long long* __restrict__ trace) {  // trace: development timestamps (SW_ATTN_TRACE) or null
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);
   uint64_t* q_full = bars;
@@ -61,6 +65,13 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = qt * TQ;
   const int n_tiles = (T + TK - 1) / TK;
+  // development: clock64 stamps of one CTA in the middle of the grid: [role 0 = softmax warp 2 lane 0,
+  // role 1 = MMA thread][tile][event]
+  const bool tr = trace && blockIdx.x == 5 && blockIdx.y == 7 && blockIdx.z == (gridDim.z >> 1);
+#define ATT_TRACE(role, tile, ev)                                                        \
+  do {                                                                                   \
+    if (tr) trace[((role) * 16 + (tile)) * 8 + (ev)] = clock64();                        \
+  } while (0)
   const int row_base = w * T;
 
   if (threadIdx.x == 0) {
@@ -76,7 +87,7 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
       mbar_init(&kv_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_ready, 4);
+    mbar_init(p_ready, 8);  // one arrive per softmax warp
     mbar_init(&o_full[0], 1);
     mbar_init(&o_full[1], 1);
     fence_mbar_init();
@@ -125,8 +136,10 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         const uint32_t sv = smem_u32(smem + SM_V + s * TILE_BYTES);
+        ATT_TRACE(1, j, 0);
         mbar_wait(p_ready, j & 1);
         tc_fence_after();
+        ATT_TRACE(1, j, 1);
         mbar_wait(&v_full[s], ph);
         tc_fence_after();
 #pragma unroll
@@ -140,132 +153,140 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
         umma_commit(&kv_empty[s]);
         // S is free again (the softmax warps signalled p_ready after their last read): queue the next
         // score tile right behind, it runs while they fold O_{j-1} and wait
+        ATT_TRACE(1, j, 2);
         if (j + 1 < n_tiles) issue_s(j + 1);
+        ATT_TRACE(1, j, 3);
       }
     }
   } else {
-    // ---------------- softmax warps: thread = one query row = one TMEM lane
-    const int qd = warp & 3;
+    // ---------------- softmax warps: TWO threads per query row (= TMEM lane): warps 2-5 take keys 0..63 of
+    // every 128-key tile and output dims 0..31, warps 6-9 keys 64..127 and dims 32..63. Generation 2 had one
+    // thread per row: two softmax warps per scheduler (two CTAs per SM) left every pipe under 42 % busy
+    // (MUFU 42 %, ALU 40 %, FMA 21 %, issue 54 %; profiles/r1_ncu_attn_tc_v2.txt) - latency-bound.
+    const int qd = warp & 3;              // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;     // which 64 keys / 32 output dims
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const float sc = 0.125f * 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;
-    float acc[DH];
+    float acc[DH / 2];
 #pragma unroll
-    for (int i = 0; i < DH; ++i) acc[i] = 0.f;
+    for (int i = 0; i < DH / 2; ++i) acc[i] = 0.f;
     uint8_t* prow = smem + SM_P + row * 128;
+    uint16_t* xch = reinterpret_cast<uint16_t*>(smem + SM_XCH);
     float alpha_prev = 1.f;
-    // Every tcgen05.ld below is issued one chunk AHEAD of the arithmetic that consumes it (two register
-    // buffers, tcgen05.wait::ld right before the use): generation 2.0 of this kernel waited for each of its
-    // ten loads per tile (~250 cycles each, 2 500 of the ~5 000 cycles a warp spent per tile), which left
-    // the MUFU pipe - the real bound of a 64-wide head, 128 ex2 per row and tile - half idle.
-    auto fold_o = [&](int j, float a) {  // acc = acc * a + O_j
+    auto fold_o = [&](int j, float a) {  // acc = acc * a + O_j (this thread's 32 dims)
       mbar_wait(&o_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t ra[32], rb[32];
-      const uint32_t o_addr = tmem + lane_addr + 128 + (j & 1) * 64;
-      tmem_ld_32x32b_x32(o_addr, ra);
-      tmem_ld_32x32b_x32(o_addr + 32, rb);
-      tmem_ld_wait(ra);
-      tmem_ld_wait(rb);
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem + lane_addr + 128 + (j & 1) * 64 + half * 32, r);
+      tmem_ld_wait(r);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] = acc[i] * a + __uint_as_float(ra[i]);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[32 + i] = acc[32 + i] * a + __uint_as_float(rb[i]);
+      for (int i = 0; i < 32; ++i) acc[i] = acc[i] * a + __uint_as_float(r[i]);
       tc_fence_before();
     };
-    const uint32_t s_addr = tmem + lane_addr;
-    auto chunk_max = [&](const uint32_t (&r)[32], int c, int valid, float& mx) {
-      if (c * 32 + 32 <= valid) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-      }
-    };
-    auto chunk_exp = [&](const uint32_t (&r)[32], int c, int valid, float mn, float& lsum) {
-      uint32_t pk[16];
-      if (c * 32 + 32 <= valid) {  // full chunk: no masking
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
-          const float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
-          lsum += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
-          float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
-          if (c * 32 + 2 * i >= valid) p0 = 0.f;
-          if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
-          lsum += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-      }
-      // 32 keys = 4 chunks of 16 B; chunk index within the 64-key atom: (c & 1) * 4 + q
-      uint8_t* atom = prow + (c >> 1) * TILE_BYTES;
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const int ch = (c & 1) * 4 + qq;
-        *reinterpret_cast<uint4*>(atom + ((ch ^ (row & 7)) << 4)) =
-            make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
-      }
-    };
+    const uint32_t s_addr = tmem + lane_addr + half * 64;
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = min(TK, T - j * TK);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      uint32_t ra[32], rb[32];
-      // ---- pass 1: row maximum of the 128 scores
+      if (warp == 2 && lane == 0) ATT_TRACE(0, j, 0);
+      // ---- pass 1: maximum of this thread's 64 scores, then of the row
       float mx = -INFINITY;
-      tmem_ld_32x32b_x32(s_addr, ra);
-      tmem_ld_wait(ra);
-      tmem_ld_32x32b_x32(s_addr + 32, rb);
-      chunk_max(ra, 0, valid, mx);
-      tmem_ld_wait(rb);
-      tmem_ld_32x32b_x32(s_addr + 64, ra);
-      chunk_max(rb, 1, valid, mx);
-      tmem_ld_wait(ra);
-      tmem_ld_32x32b_x32(s_addr + 96, rb);
-      chunk_max(ra, 2, valid, mx);
-      tmem_ld_wait(rb);
-      tmem_ld_32x32b_x32(s_addr, ra);  // chunk 0 again, for pass 2
-      chunk_max(rb, 3, valid, mx);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(s_addr + cc * 32, r);
+        tmem_ld_wait(r);
+        if (c * 32 + 32 <= valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+      }
+      // The partner's previous read of this slot happened before it arrived on p_ready for tile j-1, and
+      // S_j (whose completion we just waited for) was issued after all eight warps had arrived: no race.
+      // Exchanged as bf16 ROUNDED UP (any upper bound of the row maximum is a valid softmax shift, and both
+      // threads of the row must use the same one): 512 bytes instead of 1 KB keep two CTAs on an SM.
+      {
+        const uint32_t u = __float_as_uint(mx);
+        uint32_t t = u & 0xffff0000u;
+        if (t != u && !(u >> 31)) t += 0x10000u;
+        mx = __uint_as_float(t);
+        xch[half * 128 + row] = static_cast<uint16_t>(t >> 16);
+      }
+      if (warp == 2 && lane == 0) ATT_TRACE(0, j, 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) ATT_TRACE(0, j, 2);
+      mx = fmaxf(mx, __uint_as_float(static_cast<uint32_t>(xch[(half ^ 1) * 128 + row]) << 16));
       const float mn = fmaxf(m, mx * sc);
       const float alpha = fast_exp2(m - mn);
       m = mn;
       // ---- pass 2: P = exp2(S * sc - m) -> bf16 -> shared memory (the A operand of P V)
       float lsum = 0.f;
-      tmem_ld_wait(ra);
-      tmem_ld_32x32b_x32(s_addr + 32, rb);
-      chunk_exp(ra, 0, valid, mn, lsum);
-      tmem_ld_wait(rb);
-      tmem_ld_32x32b_x32(s_addr + 64, ra);
-      chunk_exp(rb, 1, valid, mn, lsum);
-      tmem_ld_wait(ra);
-      tmem_ld_32x32b_x32(s_addr + 96, rb);
-      chunk_exp(ra, 2, valid, mn, lsum);
-      tmem_ld_wait(rb);
-      chunk_exp(rb, 3, valid, mn, lsum);
-      l = l * alpha + lsum;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(s_addr + cc * 32, r);
+        tmem_ld_wait(r);
+        uint32_t pk[16];
+        if (c * 32 + 32 <= valid) {  // full chunk: no masking
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
+            const float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
+            lsum += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
+            float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
+            if (c * 32 + 2 * i >= valid) p0 = 0.f;
+            if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
+            lsum += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+        }
+        // 32 keys = 4 chunks of 16 B; chunk index within the 64-key atom: (c & 1) * 4 + q
+        uint8_t* atom = prow + (c >> 1) * TILE_BYTES;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const int ch = (c & 1) * 4 + qq;
+          *reinterpret_cast<uint4*>(atom + ((ch ^ (row & 7)) << 4)) =
+              make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+        }
+      }
+      l = l * alpha + lsum;  // this thread's half of the row sum (same alpha in both halves)
+      if (warp == 2 && lane == 0) ATT_TRACE(0, j, 3);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
+      if (warp == 2 && lane == 0) ATT_TRACE(0, j, 4);
       // fold the PREVIOUS tile's O while the tensor core works on this tile's P V and the next Q K^T
       if (j > 0) fold_o(j - 1, alpha_prev);
+      if (warp == 2 && lane == 0) ATT_TRACE(0, j, 5);
       alpha_prev = alpha;
     }
     fold_o(n_tiles - 1, alpha_prev);
+    // the two halves of the row sum meet in the P tile, which is free once the last P V has completed
+    float* lx = reinterpret_cast<float*>(smem + SM_P);
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // every thread is past its wait for the last O
+    lx[half * 128 + row] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += lx[(half ^ 1) * 128 + row];
     if (q0 + row < T) {
       const float inv = 1.0f / l;
-      bf16* op = out + (int64_t)(row_base + q0 + row) * d + h * DH;
+      bf16* op = out + (int64_t)(row_base + q0 + row) * d + h * DH + half * 32;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         uint4 o;
         o.x = pack_bf16x2(acc[8 * i] * inv, acc[8 * i + 1] * inv);
         o.y = pack_bf16x2(acc[8 * i + 2] * inv, acc[8 * i + 3] * inv);
@@ -297,7 +318,29 @@ int encoder_attention_tc(const bf16* qkv, bf16* out, int n_win, int T, int d, in
   CUtensorMap map;
   if (make_tma_map_2d_bf16(&map, qkv, 3 * (int64_t)d, (int64_t)n_win * T, 3 * (int64_t)d, 64, 128)) return -1;
   dim3 grid((T + TQ - 1) / TQ, n_head, n_win);
-  encoder_attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(map, out, T, d);
+  static int trace_left = getenv("SW_ATTN_TRACE") ? 1 : 0;  // development: time one CTA of one launch
+  long long* d_trace = nullptr;
+  if (trace_left > 0 && n_win >= 8) {
+    cudaMalloc(&d_trace, 2 * 16 * 8 * sizeof(long long));
+    cudaMemset(d_trace, 0, 2 * 16 * 8 * sizeof(long long));
+  }
+  encoder_attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(map, out, T, d, d_trace);
+  if (d_trace) {
+    trace_left = 0;
+    long long h[2 * 16 * 8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d_trace);
+    const long long t00 = h[0];
+    for (int j = 0; j < 12; ++j) {
+      const long long* a = h + j * 8;
+      const long long* b = h + (16 + j) * 8;
+      fprintf(stderr, "[attn trace] tile %2d softmax: S seen %7lld | pass1 %5lld | bar %5lld | pass2 %5lld | fence+arrive %5lld | fold %5lld || "
+                      "mma: wait P from %7lld, seen %7lld, PV issued +%4lld, S(j+1) issued +%4lld\n",
+              j, a[0] - t00, a[1] - a[0], a[2] - a[1], a[3] - a[2], a[4] - a[3], a[5] - a[4], b[0] - t00, b[1] - t00,
+              b[2] - b[1], b[3] - b[2]);
+    }
+  }
   SW_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -22,12 +22,14 @@ namespace {
 
 constexpr int TQ = 128, TK = 128, DH = 64;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128 rows][64 bf16] swizzled tile
-constexpr int SM_Q = 0, SM_K = TILE_BYTES, SM_V = 3 * TILE_BYTES, SM_P = 5 * TILE_BYTES;
-constexpr int SM_BARS = 7 * TILE_BYTES;
+constexpr int SM_Q = 0, SM_K = TILE_BYTES, SM_V = 3 * TILE_BYTES;
+constexpr int SM_BARS = 5 * TILE_BYTES;
 constexpr int SM_XCH = SM_BARS + 128;  // [2 halves][128 rows] bf16: the row maxima the two threads of a row exchange
 constexpr int ATT_SMEM = SM_XCH + 512;  // two CTAs per SM: 2 x (ATT_SMEM + 1 KB reserved) <= 228 KB
 constexpr int ATT_THREADS = 320;       // warp 0: TMA, warp 1: TMEM + MMA issue, warps 2-9: softmax
-constexpr int TMEM_COLS = 256;  // S: columns [0,128), O double-buffered: [128,192) and [192,256)
+constexpr int TMEM_COLS = 256;  // S: columns [0,128), O double-buffered: [128,192) and [192,256).
+// P (bf16, two keys per 32-bit column) overwrites the scores it was computed from: keys 0..63 in columns
+// [0,32), keys 64..127 in columns [64,96) - each softmax thread only overwrites columns it has already read.
 
 // MN-major 128B-swizzled operand (the V tile: rows = keys (K), 64 dims (MN) contiguous per row):
 // canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> SBO = 1024 B between 8-key groups
@@ -119,7 +121,7 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);              // S = Q K^T, both K-major
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);  // O = P V, B (V) MN-major
-      const uint32_t sq = smem_u32(smem + SM_Q), sp = smem_u32(smem + SM_P);
+      const uint32_t sq = smem_u32(smem + SM_Q);
       mbar_wait(q_full, 0);
       auto issue_s = [&](int j) {  // S_j = Q K_j^T
         const int s = j & 1;
@@ -144,10 +146,10 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < TK / 16; ++k) {
-          // A = P: two 64-key swizzle atoms of [128 rows][128 B]; B = V: 16 keys = 2 KB per k-step
-          const uint64_t adesc = make_umma_desc_sw128(sp + (k >> 2) * TILE_BYTES) + 2 * (k & 3);
+          // A = P in tensor memory (16 keys = 8 packed columns per k-step); B = V: 16 keys = 2 KB per k-step
+          const uint32_t a_tmem = tmem + (k >> 2) * 64 + (k & 3) * 8;
           const uint64_t bdesc = make_umma_desc_mn_sw128(sv + k * 2048);
-          umma_bf16(tmem + 128 + (j & 1) * 64, adesc, bdesc, idesc_o, k != 0);
+          umma_bf16_ts(tmem + 128 + (j & 1) * 64, a_tmem, bdesc, idesc_o, k != 0);
         }
         umma_commit(&o_full[j & 1]);
         umma_commit(&kv_empty[s]);
@@ -172,7 +174,6 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
     float acc[DH / 2];
 #pragma unroll
     for (int i = 0; i < DH / 2; ++i) acc[i] = 0.f;
-    uint8_t* prow = smem + SM_P + row * 128;
     uint16_t* xch = reinterpret_cast<uint16_t*>(smem + SM_XCH);
     float alpha_prev = 1.f;
     auto fold_o = [&](int j, float a) {  // acc = acc * a + O_j (this thread's 32 dims)
@@ -254,19 +255,13 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
             pk[i] = pack_bf16x2(p0, p1);
           }
         }
-        // 32 keys = 4 chunks of 16 B; chunk index within the 64-key atom: (c & 1) * 4 + q
-        uint8_t* atom = prow + (c >> 1) * TILE_BYTES;
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          const int ch = (c & 1) * 4 + qq;
-          *reinterpret_cast<uint4*>(atom + ((ch ^ (row & 7)) << 4)) =
-              make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
-        }
+        // 32 keys = 16 packed columns of this row, over scores this thread has already consumed
+        tmem_st_32x32b_x16(s_addr + cc * 16, pk);
       }
       l = l * alpha + lsum;  // this thread's half of the row sum (same alpha in both halves)
       if (warp == 2 && lane == 0) ATT_TRACE(0, j, 3);
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
       if (warp == 2 && lane == 0) ATT_TRACE(0, j, 4);
@@ -276,8 +271,8 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
       alpha_prev = alpha;
     }
     fold_o(n_tiles - 1, alpha_prev);
-    // the two halves of the row sum meet in the P tile, which is free once the last P V has completed
-    float* lx = reinterpret_cast<float*>(smem + SM_P);
+    // the two halves of the row sum meet in the first K buffer, which is free once the last P V has completed
+    float* lx = reinterpret_cast<float*>(smem + SM_K);
     asm volatile("bar.sync 1, 256;" ::: "memory");  // every thread is past its wait for the last O
     lx[half * 128 + row] = l;
     asm volatile("bar.sync 1, 256;" ::: "memory");

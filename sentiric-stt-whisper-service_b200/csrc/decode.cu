@@ -3,19 +3,12 @@
 // argmax-or-draw kernel. Together they replace, for one batched step, the device part of
 // whisper_decode_internal and the CPU whisper_process_logits / whisper_sample_token* of
 // whisper.cpp (reference call site stt_engine.cpp:245).
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace sw {
 namespace {
 
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
   f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
   f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
@@ -32,91 +25,6 @@ __global__ void kv_copy_pages_kernel(bf16* __restrict__ pool, const int* __restr
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x)
     d[i] = s[i];
 }
-
-// ---- development legacy path (SW_OLD_SA=1): separate append launch + generation-1 attention
-__device__ __forceinline__ const bf16* page_ptr_v1(const bf16* pool, const DecRow* rows_pt, int slot,
-                                                int pos, int layer, int n_layer, int kv, int d) {
-  const int page = rows_pt[slot].pages[pos / KV_PAGE];  // development legacy path: `slot` is the ROW index here
-  return pool + ((((int64_t)page * n_layer + layer) * 2 + kv) * KV_PAGE + (pos % KV_PAGE)) * d;
-}
-
-// ------------------------------------------------------------------------------------------
-__global__ void kv_append_kernel_v1(const bf16* __restrict__ qkv, const DecRow* __restrict__ rows, int d,
-                                 bf16* __restrict__ pool, const DecRow* __restrict__ rows_pt, int layer,
-                                 int n_layer) {
-  const DecRow r = rows[blockIdx.x];
-  const uint4* src = reinterpret_cast<const uint4*>(qkv + (int64_t)blockIdx.x * 3 * d + d);
-  uint4* dk = reinterpret_cast<uint4*>(const_cast<bf16*>(page_ptr_v1(pool, rows, blockIdx.x, r.pos, layer, n_layer, 0, d)));
-  uint4* dv = reinterpret_cast<uint4*>(const_cast<bf16*>(page_ptr_v1(pool, rows, blockIdx.x, r.pos, layer, n_layer, 1, d)));
-  const int nv = d / 8;
-  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-    dk[i] = src[i];
-    dv[i] = src[nv + i];
-  }
-}
-
-// one CTA (128 threads) per (row, head); n_kv = pos + 1 <= 448
-__global__ void __launch_bounds__(128)
-self_attention_kernel_v1(const bf16* __restrict__ qkv, const DecRow* __restrict__ rows, int d,
-                      const bf16* __restrict__ pool, const DecRow* __restrict__ rows_pt, int layer,
-                      int n_layer, bf16* __restrict__ out) {
-  __shared__ float qs[64];
-  __shared__ float sc[448];
-  __shared__ float red[4];
-  __shared__ float part[4][64];
-  const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
-  const DecRow row = rows[r];
-  const int n_kv = row.pos + 1;
-  if (tid < 64) qs[tid] = __bfloat162float(qkv[(int64_t)r * 3 * d + h * 64 + tid]) * 0.125f;
-  __syncthreads();
-  float lmax = -INFINITY;
-  for (int k = tid; k < n_kv; k += 128) {
-    const uint4* kp = reinterpret_cast<const uint4*>(page_ptr_v1(pool, rows, r, k, layer, n_layer, 0, d) + h * 64);
-    float acc = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float f[8];
-      bf16x8_to_f32(kp[c], f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc += qs[c * 8 + e] * f[e];
-    }
-    sc[k] = acc;
-    lmax = fmaxf(lmax, acc);
-  }
-  lmax = warp_max(lmax);
-  if ((tid & 31) == 0) red[tid >> 5] = lmax;
-  __syncthreads();
-  const float mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-  __syncthreads();
-  float lsum = 0.f;
-  for (int k = tid; k < n_kv; k += 128) {
-    const float p = __expf(sc[k] - mx);
-    sc[k] = p;
-    lsum += p;
-  }
-  lsum = warp_sum(lsum);
-  if ((tid & 31) == 0) red[tid >> 5] = lsum;
-  __syncthreads();
-  const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
-  // P.V: warp w takes keys w, w+4, ...; lane owns dims 2*lane, 2*lane+1
-  const int w = tid >> 5, lane = tid & 31;
-  float a0 = 0.f, a1 = 0.f;
-  for (int k = w; k < n_kv; k += 4) {
-    const bf16* vp = page_ptr_v1(pool, rows, r, k, layer, n_layer, 1, d) + h * 64;
-    const uint32_t u = reinterpret_cast<const uint32_t*>(vp)[lane];
-    const float p = sc[k];
-    a0 += p * __uint_as_float(u << 16);
-    a1 += p * __uint_as_float(u & 0xffff0000u);
-  }
-  part[w][2 * lane] = a0;
-  part[w][2 * lane + 1] = a1;
-  __syncthreads();
-  if (tid < 64) {
-    const float v = (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]) * inv;
-    out[(int64_t)r * d + h * 64 + tid] = __float2bfloat16_rn(v);
-  }
-}
-
 
 // one CTA (128 threads) per (row, head); n_kv = pos + 1 <= 448. The CTA also appends the row's own
 // K/V head slice to the paged cache (no separate append launch); keys of positions >= pos0 are
@@ -504,13 +412,6 @@ int self_attention(const bf16* qkv, const DecRow* d_rows, int R, int d, int n_he
                    int layer, int n_layer, bf16* out, cudaStream_t stream) {
   if (R <= 0) return 0;
   SW_CHECK(d == n_head * 64, "self_attention: head dim must be 64");
-  static const bool legacy = getenv("SW_OLD_SA") && atoi(getenv("SW_OLD_SA"));
-  if (legacy) {
-    kv_append_kernel_v1<<<R, 128, 0, stream>>>(qkv, d_rows, d, pool, d_rows, layer, n_layer);
-    self_attention_kernel_v1<<<dim3(R, n_head), 128, 0, stream>>>(qkv, d_rows, d, pool, d_rows, layer, n_layer, out);
-    SW_CUDA_CHECK(cudaGetLastError());
-    return 0;
-  }
   SW_CUDA_CHECK(launch_pdl(self_attention_kernel, dim3(R, n_head), dim3(128), 0, stream, qkv, d_rows, d, pool,
                            layer, n_layer, out));
   return 0;

@@ -303,7 +303,11 @@ def main():
         clocks=clk,
         roofline=dict(bound="hbm", kernel="cross_attention_kernel", achieved=xa_gbs, peak=pk["hbm"],
                       unit="GB/s", frac=xa_gbs / pk["hbm"], traffic=None,
-                      avg_launch_ms=xa_ms, algorithmic_bytes_per_launch=xa_bytes, peak_source=pk["src"]),
+                      avg_launch_ms=xa_ms, algorithmic_bytes_per_launch=xa_bytes, peak_source=pk["src"],
+                      note=("timed with CUDA events on lane 0's stream while the other lane's kernels share the SMs and "
+                            "HBM (the grid is capped at 96 CTAs under lanes); alone on the GPU the same kernel runs at "
+                            "0.89 of peak (profiles/r1_bench_v10.json, r1_ncu_xattn_v5.txt). stages.decode_frac_of_hbm "
+                            "is the aggregate of both lanes.") if lanes > 1 else None),
         stages=dict(
             lanes=lanes,
             lanes_note="device_ms_per_step = per-lane device time summed over lanes / lanes (lanes overlap in time)",

@@ -428,3 +428,31 @@ def test_decode_is_bit_deterministic_under_concurrent_load(swb, tiny_model):
         th.join()
     a.close()
     b.close()
+
+
+def test_config5_large_v3_batch64_properties(swb, ora):
+    """BASELINE configs[4] at full model size: Whisper large-v3 (128 mel, 32 + 32 layers, d = 1280), greedy with
+    the service's parameters, 72 x 30 s windows through a two-lane context with batches of up to 64. Size-
+    independent properties over all windows (scripted transcript followed, duplicates bit-identical, segment
+    times tile the window, 128-bin front end) and one window compared token by token, time by time with the
+    CPU oracle."""
+    path, info = model_file("large-v3", script_len=60)
+    e = swb.Engine(path, max_batch=64, max_beams=5)
+    assert e.info.n_mels == 128 and e.info.n_text_layer == 32
+    clips = [synth_audio.utterance(5, i) for i in range(70)] + [synth_audio.utterance(5, 0), synth_audio.utterance(5, 1)]
+    pe = e.default_params(0, language="en", token_timestamps=1, suppress_nst=1, no_speech_thold=0.85,
+                          logprob_thold=-0.7, entropy_thold=2.4, temperature=0.0)  # stt_engine.cpp:204-243
+    got = e.full_batch_pcm16(clips, pe)
+    sp, script = info["special"], info["script"]
+    kept = [t for i, t in enumerate(script[:-1]) if not (i > 0 and t >= sp["beg"] and script[i - 1] == t)]
+    assert sum(seg_ids(g) == kept for g in got) >= 71  # >= 99 % of segments token-identical
+    assert seg_ids(got[0]) == seg_ids(got[70]) and seg_ids(got[1]) == seg_ids(got[71])
+    for g in got:
+        assert g["segments"][0]["t0"] == 0 and g["segments"][-1]["t1"] == 3000
+    o = ora.Oracle(path, weight_round=False, act_round=ora.ACT_F16)
+    po = o.default_params(0, language="en", token_timestamps=1, suppress_nst=1, no_speech_thold=0.85,
+                          logprob_thold=-0.7, entropy_thold=2.4, temperature=0.0)
+    compare_results(got[7], o.full(synth_audio.to_f32(clips[7]), po))
+    st = e.stats()
+    assert st["n_lanes"] == 2 and st["n_windows"] == 72
+    e.close()

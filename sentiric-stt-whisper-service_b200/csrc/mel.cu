@@ -101,14 +101,52 @@ mel_log_power_kernel(const void* __restrict__ pcm, const MelUtt* __restrict__ ut
 
   if (tid < N1) tw16[tid] = tabs.tw16[tid];
   if (tid >= 32 && tid < 32 + N2) tw25[tid - 32] = tabs.tw25[tid - 32];
-  // framing: padded index p = f*160 + n; p < 200 reflects (pcm[200 - p]); else pcm[p - 200]; 0 past the end
-  for (int i = tid; i < MEL_N_FFT * FR; i += 256) {
-    const int n = i / FR, fr = i % FR;
-    const int p = (f0 + fr) * MEL_HOP + n;
-    const int s = p < 200 ? 200 - p : p - 200;
-    float v = 0.f;
-    if (f0 + fr < u.n_active && s < u.n_samples) v = load_sample<F32>(pcm, u.pcm_off, s);
-    xs[i] = tabs.hann[n] * v;
+  // framing: padded index p = f*160 + n; p < 200 reflects (pcm[200 - p]); else pcm[p - 200]; 0 past the end.
+  // The 8 frames of the CTA cover 1520 consecutive padded samples: they are staged in shared memory once,
+  // with 16-byte loads (8 int16 or 2 x float4; the span starts at a multiple of 8 samples), the int16 -> f32
+  // / 32768 of transcribe_pcm16 applied in registers, and every frame is windowed out of that copy.
+  {
+    constexpr int SPAN = (FR - 1) * MEL_HOP + MEL_N_FFT;  // 1520
+    float* raw = zs;                                      // stage A's output buffer is free until then
+    const int p0 = f0 * MEL_HOP;
+    if (p0 >= 200) {
+      const int s0 = p0 - 200;
+      for (int v = tid; v < SPAN / 8; v += 256) {
+        const int sidx = s0 + v * 8;
+        float x[8];
+        if (sidx + 8 <= u.n_samples) {
+          if (F32) {
+            const float4* gp = reinterpret_cast<const float4*>(static_cast<const float*>(pcm) + u.pcm_off + sidx);
+            const float4 a = __ldg(gp), b = __ldg(gp + 1);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+          } else {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(static_cast<const int16_t*>(pcm) + u.pcm_off + sidx));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              x[2 * e] = static_cast<float>(static_cast<int16_t>(w[e] & 0xffffu)) / 32768.0f;
+              x[2 * e + 1] = static_cast<float>(static_cast<int16_t>(w[e] >> 16)) / 32768.0f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = sidx + e < u.n_samples ? load_sample<F32>(pcm, u.pcm_off, sidx + e) : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) raw[v * 8 + e] = x[e];
+      }
+    } else {  // the first CTA of an utterance: reflected head
+      for (int q = tid; q < SPAN; q += 256) {
+        const int p = p0 + q;
+        const int sidx = p < 200 ? 200 - p : p - 200;
+        raw[q] = sidx < u.n_samples ? load_sample<F32>(pcm, u.pcm_off, sidx) : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < MEL_N_FFT * FR; i += 256) {
+      const int n = i / FR, fr = i % FR;
+      xs[i] = f0 + fr < u.n_active ? tabs.hann[n] * raw[fr * MEL_HOP + n] : 0.f;
+    }
   }
   __syncthreads();
 

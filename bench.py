@@ -302,7 +302,11 @@ def main():
                                        "seeded decoder is scripted to follow (tests compare with the CPU oracle)"),
         clocks=clk,
         roofline=dict(bound="hbm", kernel="cross_attention_kernel", achieved=xa_gbs, peak=pk["hbm"],
-                      unit="GB/s", frac=xa_gbs / pk["hbm"], traffic=None,
+                      unit="GB/s", frac=xa_gbs / pk["hbm"],
+                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+                      # (profiles/r1_ncu_xattn_v5.txt: 491.95 MB read = the algorithmic bytes, 20.1 MB of partials
+                      # written; large-v3, 64 windows, one lane)
+                      traffic=512.0e6 if (args.model == "large-v3" and args.batch == 64) else None,
                       avg_launch_ms=xa_ms, algorithmic_bytes_per_launch=xa_bytes, peak_source=pk["src"],
                       note=("timed with CUDA events on lane 0's stream while the other lane's kernels share the SMs and "
                             "HBM (the grid is capped at 96 CTAs under lanes); alone on the GPU the same kernel runs at "

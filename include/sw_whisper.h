@@ -200,6 +200,16 @@ SW_API int sw_prosody_segments_pcm16(sw_ctx* ctx, const int16_t* pcm, int64_t n_
                                      const int64_t* seg_begin, const int64_t* seg_end, int n_segs,
                                      const sw_prosody_opts* opts, sw_prosody* out);
 
+/* ---- sample-rate conversion -------------------- *
+ * stands in for SttEngine::resample_audio (stt_engine.cpp:87-115, libsamplerate
+ * src_simple(SRC_SINC_FASTEST), called at :138-145 for inputs that are not
+ * 16 kHz). libsamplerate is not in the reference tree: the same published
+ * method (windowed-sinc band-limited interpolation) with its own window;
+ * parity with libsamplerate is not claimed (> 89 dB tone SNR instead). */
+SW_API int64_t sw_resample_out_len(int64_t n_in, int sr_in, int sr_out); /* floor(n_in * sr_out / sr_in) */
+/* in: n_in samples (host or device); out: sw_resample_out_len samples (host or device) */
+SW_API int sw_resample_f32(sw_ctx* ctx, const float* in, int64_t n_in, int sr_in, int sr_out, float* out);
+
 /* ---- stage-level hooks (parity tests and roofline measurement) --------- *
  * Host pointers in, host pointers out, synchronous. */
 /* log-mel of one utterance (whisper.cpp log_mel_spectrogram): out is

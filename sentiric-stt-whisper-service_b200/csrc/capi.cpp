@@ -87,6 +87,7 @@ void sw_ctx_destroy(sw_ctx* ctx) {
     cudaSetDevice(ctx->e->device);
     cudaDeviceSynchronize();
     sw::prosody_state_free(ctx->prosody);
+    sw::resample_state_free(ctx->resample);
     for (Engine* l : ctx->lanes) delete l;
     delete ctx->e;
   }

@@ -137,6 +137,11 @@ int prosody_frames(const void* d_pcm, int is_f32, const ProsodySeg* d_segs, int 
 int prosody_reduce(const ProsodySeg* d_segs, const ProsodyFrame* d_frames, int n_segs, int shift, int sample_rate,
                    float min_pitch, float max_pitch, ProsodyRaw* d_out, cudaStream_t stream);
 
+// ------------------------------------------------------------------ sample-rate conversion (resample.cu)
+constexpr int RS_ZEROS = 16, RS_GRID = 256;  // zero crossings per side of the windowed sinc, table points per crossing
+int resample_f32(const float* d_in, int64_t n_in, int sr_in, int sr_out, const float* d_table, float scale,
+                 float gscale, int half, int64_t n_out, float* d_out, cudaStream_t stream);
+
 // logit rules + log-softmax + pick (whisper_process_logits + whisper_sample_token)
 struct LogitRow {        // per-row rule state, built by the host sequencer
   int is_initial;        // no token sampled yet in this window

@@ -9,6 +9,7 @@ struct sw_ctx {
   sw::Engine* e = nullptr;            // lane 0: owns the model; the stage hooks run here
   std::vector<sw::Engine*> lanes;     // further lanes: own buffers and stream, weights shared with e
   void* prosody = nullptr;            // sw::ProsodyState (prosody_host.cpp), created on first use
+  void* resample = nullptr;           // sw::ResampleState (resample_host.cpp), created on first use
 };
 struct sw_segment {
   int64_t t0 = 0, t1 = 0;
@@ -34,4 +35,5 @@ int run_full_batch_lanes(sw_ctx* ctx, const sw_full_params* params, const void* 
                          int n, bool is_f32, sw_result** out);
 const char* last_error_string();
 void prosody_state_free(void* p);
+void resample_state_free(void* p);
 }  // namespace sw

@@ -31,7 +31,7 @@ static std::string json_escape(const std::string& s) {
 
 int main(int argc, char** argv) {
   if (argc < 4) {
-    fprintf(stderr, "usage: %s <model_dir> <model_file> <pcm16.raw> [n_concurrent] [beam] [stream]\n", argv[0]);
+    fprintf(stderr, "usage: %s <model_dir> <model_file> <pcm16.raw> [n_concurrent] [beam] [stream|batch] [sample_rate]\n", argv[0]);
     return 2;
   }
   Settings s;
@@ -48,6 +48,7 @@ int main(int argc, char** argv) {
   std::vector<int16_t> pcm(raw.size() / 2);
   memcpy(pcm.data(), raw.data(), pcm.size() * 2);
   const bool stream_mode = argc > 6 && std::string(argv[6]) == "stream";
+  const int sample_rate = argc > 7 ? atoi(argv[7]) : 16000;
   if (stream_mode) {
     // n_conc concurrent streams (grpc_server.cpp:129-305 policy through StreamSession), each fed the clip in
     // 0.5 s chunks and closed with an empty chunk: their re-transcriptions meet in the dispatcher
@@ -92,7 +93,7 @@ int main(int argc, char** argv) {
     std::vector<SttEngine::PerformanceMetrics> met(n_conc);
     std::vector<std::thread> th;
     for (int i = 0; i < n_conc; ++i)
-      th.emplace_back([&, i] { out[i] = engine.transcribe_pcm16(pcm, 16000, RequestOptions(), &met[i]); });
+      th.emplace_back([&, i] { out[i] = engine.transcribe_pcm16(pcm, sample_rate, RequestOptions(), &met[i]); });
     for (auto& t : th) t.join();
     for (int i = 0; i < n_conc; ++i) {
       printf("{\"request\": %d, \"token_count\": %d, \"batches_run\": %ld, \"segments\": [", i, met[i].token_count,

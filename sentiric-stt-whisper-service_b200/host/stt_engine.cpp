@@ -158,11 +158,15 @@ std::vector<TranscriptionResult> SttEngine::transcribe(const std::vector<float>&
                                                        const RequestOptions& options,
                                                        PerformanceMetrics* out_metrics) {
   const auto t_start = Clock::now();
-  if (input_sample_rate != 16000) {
-    // :138-145 resamples with libsamplerate (SRC_SINC_FASTEST); that codec-side step is outside the
-    // hot path and the library is not available: refuse loudly.
-    throw std::invalid_argument("SttEngine: only 16 kHz input is supported by this build (got " +
-                                std::to_string(input_sample_rate) + " Hz)");
+  if (input_sample_rate != 16000 && ctx_ && !pcmf32.empty() && input_sample_rate > 0) {
+    // :138-145 resamples with libsamplerate (SRC_SINC_FASTEST); here the engine's own windowed-sinc
+    // converter on the GPU (sw_resample_f32: same method, own window). Like the
+    // reference, a failed conversion falls through to the unconverted samples (:141-144).
+    std::vector<float> resampled((size_t)sw_resample_out_len((int64_t)pcmf32.size(), input_sample_rate, 16000));
+    if (!resampled.empty() && sw_resample_f32(ctx_, pcmf32.data(), (int64_t)pcmf32.size(), input_sample_rate, 16000,
+                                              resampled.data()) == 0)
+      return run_request(resampled.data(), resampled.size(), nullptr, options, out_metrics, t_start);
+    fprintf(stderr, "[stt_engine] resampling %d -> 16000 Hz failed: %s\n", input_sample_rate, sw_last_error());
   }
   return run_request(pcmf32.data(), pcmf32.size(), nullptr, options, out_metrics, t_start);
 }

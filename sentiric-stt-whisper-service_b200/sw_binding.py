@@ -84,6 +84,7 @@ EXPORTS = [
     "sw_result_lang_id", "sw_result_n_decode_steps", "sw_result_n_windows", "sw_result_free",
     "sw_ctx_get_stats", "sw_ctx_set_kernel_timing", "sw_mel_pcm16", "sw_mel_f32", "sw_encode", "sw_decode_logits",
     "sw_prosody_default_opts", "sw_prosody_segments_f32", "sw_prosody_segments_pcm16",
+    "sw_resample_out_len", "sw_resample_f32",
     "sw_dev_gemm_bf16", "sw_dev_skinny_gemm", "sw_dev_skinny_split", "sw_dev_layer_norm"]
 
 _lib = None
@@ -302,6 +303,17 @@ class Engine:
                 d[f] = float(getattr(p, f))
             res.append(d)
         return res
+
+    def resample(self, pcm, sr_in, sr_out=16000):
+        a = np.ascontiguousarray(pcm, np.float32)
+        self.L.sw_resample_out_len.restype = C.c_int64
+        self.L.sw_resample_out_len.argtypes = [C.c_int64, C.c_int, C.c_int]
+        out = np.empty(self.L.sw_resample_out_len(len(a), sr_in, sr_out), np.float32)
+        self.L.sw_resample_f32.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.c_int, C.c_int,
+                                           C.POINTER(C.c_float)]
+        if len(a) and self.L.sw_resample_f32(self.h, _fp(a), len(a), sr_in, sr_out, _fp(out)):
+            raise RuntimeError(last_error())
+        return out
 
     def set_kernel_timing(self, on):
         self.L.sw_ctx_set_kernel_timing(self.h, int(on))

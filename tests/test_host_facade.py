@@ -108,3 +108,24 @@ def test_concurrent_streams_share_device_passes(tmp_path):
     assert o["batches_run"] < o["transcribe_calls"] // 2           # concurrent streams shared device passes
     assert o["partials"] >= 10
     assert all(f == want for f in o["finals"]), (o["finals"], want)
+
+
+@pytest.mark.gpu
+def test_facade_resamples_non_16k_input(tmp_path):
+    """stt_engine.cpp:138-145: input that is not 16 kHz is converted first (here by sw_resample_f32): a 48 kHz
+    copy of a clip transcribes to the same tokens as the clip."""
+    from scipy.signal import resample_poly
+    build_host()
+    path, info = model_file("tiny")
+    clip = synth_audio.utterance(3, 23, seconds=9.0)
+    clip48 = np.clip(np.round(resample_poly(clip.astype(np.float64), 3, 1)), -32768, 32767).astype(np.int16)
+    outs = []
+    for name, data, rate in (("a.raw", clip, 16000), ("b.raw", clip48, 48000)):
+        raw = tmp_path / name
+        data.tofile(raw)
+        r = subprocess.run([os.path.join(HOST, "build", "stt_cli"), os.path.dirname(path), os.path.basename(path),
+                            str(raw), "1", "1", "batch", str(rate)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(json.loads(r.stdout.strip().splitlines()[0]))
+    toks = [[t[0] for s in o["segments"] for t in s["tokens"]] for o in outs]
+    assert toks[0] and toks[0] == toks[1]

@@ -5,7 +5,7 @@
 // windowed-sinc table, linear interpolation between table points, cut-off scaled by the ratio when
 // downsampling) with its own 16-zero-crossing Kaiser(9) window: > 89 dB tone SNR for 8 / 22.05 / 44.1 / 48 kHz
 // -> 16 kHz. One thread per output sample, taps walked left to right in single precision without FMA
-// contraction, so that oracle/resample_oracle.cpp defines the result bit for bit.
+// contraction, so that the CPU statement of this converter kept with the tests defines the result bit for bit.
 #include "common.cuh"
 #include "kernels.cuh"
 

@@ -3,7 +3,7 @@
 // RIFF/WAVE chunk walk, 16-bit PCM only, stereo mixed to mono as (l + r) / 2, more channels -> channel 0.
 // The reference tries ffmpeg on input without a RIFF header and otherwise assumes raw 16 kHz mono int16;
 // ffmpeg is not part of this tree, so the fallback is the raw-PCM assumption directly.
-// Pinned against the reference's own code: tests/test_wav.py compares with oracle/_ref/libref_wav.so.
+// Pinned against the reference's own code: tests/test_wav.py compares with a build of the reference's utils.h.
 #pragma once
 #include <cstdint>
 #include <cstring>

@@ -21,3 +21,6 @@ extern "C" long ref_parse_wav(const char* bytes, size_t n, short* out, size_t ca
     return -1;
   }
 }
+
+// the segment post-filter of stt_engine.cpp:272-278 (utils.h:214-306), for tests/test_text_filters.py
+extern "C" int ref_is_hallucination(const char* text) { return sentiric::utils::is_hallucination(std::string(text)) ? 1 : 0; }

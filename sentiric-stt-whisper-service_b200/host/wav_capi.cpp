@@ -17,3 +17,8 @@ extern "C" __attribute__((visibility("default"))) long stt_parse_wav(const char*
     return -1;
   }
 }
+
+#include "text_filters.h"
+extern "C" __attribute__((visibility("default"))) int stt_is_hallucination(const char* text) {
+  return sentiric::utils::is_hallucination(std::string(text)) ? 1 : 0;
+}

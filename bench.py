@@ -197,7 +197,10 @@ def main():
     from tools import synth_audio
     eng = swb.Engine(path, device=local_rank, max_batch=args.batch, max_beams=5)
     params = eng.default_params(0, **SERVICE_PARAMS)  # greedy, best_of 5, temperature_inc 0.2 (defaults)
-    params.n_threads = min(16, os.cpu_count() or 4)  # host sequencer workers (Settings.n_threads knob)
+    # host sequencer workers (the Settings.n_threads knob): this rank's share of the box's cores
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    cores_here = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
+    params.n_threads = max(2, min(16, cores_here // max(1, local_world)))
     eng.set_kernel_timing(True)
 
     # ---- inputs: W windows of 30 s int16, pinned host copy + device copy
@@ -236,28 +239,39 @@ def main():
             L.sw_result_free(r)
         return n_tok
 
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
     def timed(ptrs, k):
+        """K steps between a barrier + device synchronize on both sides, timed with two CUDA events. The device
+        is idle when the first is recorded (synchronize just before) and every step call returns only after
+        its last kernel and read-back have completed (the sequencer reads the picks of every decoder step), so
+        the second event, recorded behind the last step, closes the region on the device. The host clock
+        around the same region is reported next to it (`host_ms_per_step`); the two must agree."""
         barrier()
         t0 = time.perf_counter()
+        ev0.record()
         n_tok = 0
         for _ in range(k):
             n_tok += step(ptrs)
+        ev1.record()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        wall = time.perf_counter() - t0
+        dt = ev0.elapsed_time(ev1) * 1e-3
         if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            t = torch.tensor([dt, wall], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return dt, n_tok
+            dt, wall = float(t[0].item()), float(t[1].item())
+        return dt, n_tok, wall
 
     for i in range(args.warmup):
         step(dev_ptrs, check=(i == 0))  # untimed: every window of the first warm-up pass is checked
     eng.stats(reset=True)
     clocks = ClockSampler(local_rank)
-    clocks.start()
-    dt, n_tok = timed(dev_ptrs, args.steps)
+    if rank == 0:  # one sampler per job: the line reports rank 0's GPU, and nvidia-smi polling is not free
+        clocks.start()
+    dt, n_tok, wall = timed(dev_ptrs, args.steps)
     st = eng.stats(reset=True)
-    dt_e2e, _ = timed(host_ptrs, args.steps)
+    dt_e2e, _, wall_e2e = timed(host_ptrs, args.steps)
     st_e2e = eng.stats(reset=True)
     clk = clocks.stop()
 
@@ -285,6 +299,8 @@ def main():
     line = dict(
         metric="audio-sec/sec (RTFx)", value=value, unit="audio-sec/sec", n_gpus=world,
         steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * dt / args.steps,
+        host_ms_per_step=1e3 * wall / args.steps,
+        timing="CUDA events around the K steps, max over ranks (host clock of the same region: host_ms_per_step)",
         higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16 (f32 accumulate)",
         data="synthetic",
         config=dict(workload="whisper %s greedy batch-%d, %d x 30 s windows per GPU per step "
@@ -292,6 +308,7 @@ def main():
                     windows_per_gpu=W, batch=args.batch, script_tokens=args.script_len,
                     params="SttEngine defaults: greedy, token_timestamps, suppress_nst, temperature_inc 0.2",
                     lanes="%d lanes (batches in flight) x batch %d" % (lanes, args.batch),
+                    host_threads=int(params.n_threads),
                     l2="per-step working set (cross-KV %.1f GB) exceeds the 126 MB L2" %
                        (Ld * 2 * 1500 * d * 2 * args.batch / 1e9)),
         e2e=dict(value=e2e, unit="audio-sec/sec",

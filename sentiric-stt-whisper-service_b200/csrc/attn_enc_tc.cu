@@ -1,13 +1,16 @@
-// Encoder self-attention, generation 2: flash attention on the 5th-generation tensor cores.
+// Encoder self-attention: flash attention on the 5th-generation tensor cores.
 // One CTA = (window, head, 128-query tile); keys/values stream in 128-key tiles:
 //   warp 0 : TMA producer (Q once, then K/V tiles into a 2-stage ring; 128B-swizzled boxes of the
 //            packed [Q | K | V] activation, no separate transposes)
-//   warp 1 : tcgen05.mma issuer - S = Q K^T (128x128x64, both operands K-major) into TMEM, and
-//            O_j = P V_j (128x64x128) with V consumed MN-major straight from its [key][dim] tile
-//   warps 2..5 : softmax. Thread i owns query row i = TMEM lane i: reads S with tcgen05.ld, keeps the
-//            running max / sum, writes P as bf16 into the swizzled smem tile the second MMA reads,
-//            then folds O_j into its f32 register accumulator (acc = acc * alpha + O_j), so TMEM is
-//            never read-modify-written.
+//   warp 1 : tcgen05.mma issuer (one thread chosen by elect.sync) - S = Q K^T (128x128x64, both operands
+//            K-major) into TMEM, and O_j = P V_j (128x64x128): P read from tensor memory (TS form), V consumed
+//            MN-major straight from its [key][dim] tile
+//   warps 2..9 : softmax, two threads per query row (= TMEM lane): read S with tcgen05.ld, keep the running
+//            max / sum, write P as bf16 into P's TMEM columns with tcgen05.st, then fold O_j into an f32
+//            register accumulator (acc = acc * alpha + O_j), so TMEM is never read-modify-written.
+// Order of a key tile: the moment the softmax threads have read S(j) (= P(j) written) the issuer queues
+// S(j+1) and only then P V(j); the serial chain is softmax -> S(j+1), while P V(j) and the fold of O(j-1) run in
+// its shadow and meet it again at pass 2 of tile j+1, which needs P's columns back.
 // Two CTAs share an SM (112 KB smem, 256 TMEM columns each): one CTA's softmax overlaps the other's
 // MMAs. Replaces ggml's flash_attn_ext in whisper_encode_internal; generation 1
 // (attn_enc.cu, mma.sync) reached 298 TFLOP/s and was 35 % of the encoder time.
@@ -27,9 +30,11 @@ constexpr int SM_BARS = 5 * TILE_BYTES;
 constexpr int SM_XCH = SM_BARS + 128;  // [2 halves][128 rows] bf16: the row maxima the two threads of a row exchange
 constexpr int ATT_SMEM = SM_XCH + 512;  // two CTAs per SM: 2 x (ATT_SMEM + 1 KB reserved) <= 228 KB
 constexpr int ATT_THREADS = 320;       // warp 0: TMA, warp 1: TMEM + MMA issue, warps 2-9: softmax
-constexpr int TMEM_COLS = 256;  // S: columns [0,128), O double-buffered: [128,192) and [192,256).
-// P (bf16, two keys per 32-bit column) overwrites the scores it was computed from: keys 0..63 in columns
-// [0,32), keys 64..127 in columns [64,96) - each softmax thread only overwrites columns it has already read.
+// Tensor memory: S (f32 scores, 128 keys) | P (bf16, two keys per 32-bit column: 64 columns) | O (f32, 64 dims).
+// P has its own columns so that S(j+1) can be computed while P V(j) still reads P(j). (An earlier layout kept P
+// over the scores it came from and double-buffered O instead: P V(j) then had to be issued BEFORE S(j+1) and sat
+// on the serial chain; 1.44 vs 1.37 ms per layer for 64 windows.)
+constexpr int TMEM_COLS = 256, TM_P = 128, TM_O = 192;
 
 // MN-major 128B-swizzled operand (the V tile: rows = keys (K), 64 dims (MN) contiguous per row):
 // canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> SBO = 1024 B between 8-key groups
@@ -60,11 +65,12 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
   uint64_t* kv_empty = bars + 5;  // [2]
   uint64_t* s_full = bars + 7;
   uint64_t* p_ready = bars + 8;
-  uint64_t* o_full = bars + 9;  // [2]
+  uint64_t* o_full = bars + 9;   // P V(j) has completed: O(j) can be folded, P's columns can be rewritten
+  uint64_t* o_free = bars + 10;  // the softmax threads have folded O(j-1): P V(j) may overwrite O
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int qt = blockIdx.x, h = blockIdx.y, w = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp: provably uniform
   const int q0 = qt * TQ;
   const int n_tiles = (T + TK - 1) / TK;
   // development: clock64 stamps of one CTA in the middle of the grid: [role 0 = softmax warp 2 lane 0,
@@ -90,8 +96,8 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
     }
     mbar_init(s_full, 1);
     mbar_init(p_ready, 8);  // one arrive per softmax warp
-    mbar_init(&o_full[0], 1);
-    mbar_init(&o_full[1], 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 8);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -104,7 +110,7 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, TILE_BYTES);
       tma_load_2d(smem + SM_Q, &map_qkv, q_full, h * DH, row_base + q0);
       for (int j = 0; j < n_tiles; ++j) {
@@ -118,7 +124,10 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // elect.sync, not `lane == 0`: ptxas then knows a single thread runs the branch and emits each tcgen05.mma
+    // once; under a lane test it wraps every one in a loop over the active lanes (R2UR, ELECT, BRA.U.ANY:
+    // ~110 cycles per MMA, which was the whole "MMA dispatch" share of a key tile)
+    if (elect_one_sync()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);              // S = Q K^T, both K-major
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);  // O = P V, B (V) MN-major
       const uint32_t sq = smem_u32(smem + SM_Q);
@@ -142,21 +151,22 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
         mbar_wait(p_ready, j & 1);
         tc_fence_after();
         ATT_TRACE(1, j, 1);
+        // every softmax thread is past its last read of S(j): the next scores go first, so that the serial chain
+        // of a key tile is softmax -> S(j+1) and P V(j) runs in its shadow
+        if (j + 1 < n_tiles) issue_s(j + 1);
+        ATT_TRACE(1, j, 2);
+        mbar_wait(o_free, j & 1);
+        tc_fence_after();
         mbar_wait(&v_full[s], ph);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < TK / 16; ++k) {
           // A = P in tensor memory (16 keys = 8 packed columns per k-step); B = V: 16 keys = 2 KB per k-step
-          const uint32_t a_tmem = tmem + (k >> 2) * 64 + (k & 3) * 8;
           const uint64_t bdesc = make_umma_desc_mn_sw128(sv + k * 2048);
-          umma_bf16_ts(tmem + 128 + (j & 1) * 64, a_tmem, bdesc, idesc_o, k != 0);
+          umma_bf16_ts(tmem + TM_O, tmem + TM_P + k * 8, bdesc, idesc_o, k != 0);
         }
-        umma_commit(&o_full[j & 1]);
+        umma_commit(o_full);
         umma_commit(&kv_empty[s]);
-        // S is free again (the softmax warps signalled p_ready after their last read): queue the next
-        // score tile right behind, it runs while they fold O_{j-1} and wait
-        ATT_TRACE(1, j, 2);
-        if (j + 1 < n_tiles) issue_s(j + 1);
         ATT_TRACE(1, j, 3);
       }
     }
@@ -177,16 +187,17 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
     uint16_t* xch = reinterpret_cast<uint16_t*>(smem + SM_XCH);
     float alpha_prev = 1.f;
     auto fold_o = [&](int j, float a) {  // acc = acc * a + O_j (this thread's 32 dims)
-      mbar_wait(&o_full[j & 1], (j >> 1) & 1);
+      mbar_wait(o_full, j & 1);
       tc_fence_after();
       uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem + lane_addr + 128 + (j & 1) * 64 + half * 32, r);
+      tmem_ld_32x32b_x32(tmem + lane_addr + TM_O + half * 32, r);
       tmem_ld_wait(r);
 #pragma unroll
       for (int i = 0; i < 32; ++i) acc[i] = acc[i] * a + __uint_as_float(r[i]);
       tc_fence_before();
     };
     const uint32_t s_addr = tmem + lane_addr + half * 64;
+    const uint32_t p_addr = tmem + lane_addr + TM_P + half * 32;  // this thread's 64 probabilities: 32 packed columns
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = min(TK, T - j * TK);
       mbar_wait(s_full, j & 1);
@@ -227,6 +238,10 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
       const float mn = fmaxf(m, mx * sc);
       const float alpha = fast_exp2(m - mn);
       m = mn;
+      if (j > 0) {  // P's columns are free once P V(j-1) has completed (it was queued a whole softmax ago)
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
       // ---- pass 2: P = exp2(S * sc - m) -> bf16 -> shared memory (the A operand of P V)
       float lsum = 0.f;
 #pragma unroll
@@ -256,7 +271,7 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
           }
         }
         // 32 keys = 16 packed columns of this row, over scores this thread has already consumed
-        tmem_st_32x32b_x16(s_addr + cc * 16, pk);
+        tmem_st_32x32b_x16(p_addr + cc * 16, pk);
       }
       l = l * alpha + lsum;  // this thread's half of the row sum (same alpha in both halves)
       if (warp == 2 && lane == 0) ATT_TRACE(0, j, 3);
@@ -267,6 +282,8 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
       if (warp == 2 && lane == 0) ATT_TRACE(0, j, 4);
       // fold the PREVIOUS tile's O while the tensor core works on this tile's P V and the next Q K^T
       if (j > 0) fold_o(j - 1, alpha_prev);
+      __syncwarp();  // O is free: P V(j), queued behind S(j+1), may overwrite it
+      if (lane == 0) mbar_arrive(o_free);
       if (warp == 2 && lane == 0) ATT_TRACE(0, j, 5);
       alpha_prev = alpha;
     }

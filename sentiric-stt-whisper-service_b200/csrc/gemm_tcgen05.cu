@@ -64,7 +64,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-  const int warp_idx = threadIdx.x >> 5;
+  const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
@@ -96,7 +96,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // (elect.sync, not a lane test: ptxas then emits each UTMALDG / UTCHMMA once; under `lane == 0` it wraps every
+    // one in a loop over the active lanes - R2UR, ELECT, BRA.U.ANY - about 100 cycles per instruction)
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -120,7 +122,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;

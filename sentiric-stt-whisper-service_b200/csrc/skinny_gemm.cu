@@ -69,7 +69,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const int n0 = blockIdx.x * BN;
   const int k_begin = blockIdx.y * k_slice;
   const int r0 = blockIdx.z * SK_BM;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // warp: provably uniform
   const int n_kb = k_slice / SK_BK;
 
   pdl_launch_dependents();
@@ -85,7 +85,9 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   __syncthreads();
 
   if (warp == SK_CONSUMERS) {
-    if (lane == 0) {
+    // elect.sync rather than a lane test: ptxas then emits each TMA instruction once instead of inside a loop over
+    // the active lanes (R2UR + ELECT + BRA.U.ANY around every UTMALDG)
+    if (elect_one_sync()) {
       // weights first (independent of the predecessor), activations once it has finished
       const int pre = n_kb < SK_STAGES ? n_kb : SK_STAGES;
       for (int kb = 0; kb < pre; ++kb) {

@@ -51,7 +51,7 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * stage_bytes);
   uint64_t* empty = full + n_stages;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp: provably uniform
   const int row_f = d + 2 * n_head;  // floats per (row, chunk) partial
 
   pdl_launch_dependents();
@@ -68,7 +68,7 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
   if (warp == n_cons) {
     // no pdl_wait here: the cross-KV cache and the group tables were complete before the step's
     // first kernel started; the loads only fill this CTA's own shared memory
-    if (lane == 0) {
+    if (elect_one_sync()) {  // not a lane test: one UTMALDG per load instead of a loop over the active lanes
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int g = item / n_chunks, chunk = item - g * n_chunks;

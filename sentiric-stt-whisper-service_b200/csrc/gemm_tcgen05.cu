@@ -25,6 +25,8 @@
 #include "common.cuh"
 #include "gemm.cuh"
 
+#include <stdlib.h>
+
 #include <mutex>
 
 namespace sw {
@@ -59,6 +61,128 @@ struct EpiParams {
   int res_mod;
   int flags;
 };
+
+// Epilogue of one accumulator tile for one warp: `row` is the output row this thread owns (its TMEM lane),
+// `tmem_acc` the accumulator's address with the warp's lane quarter in the upper half, `n0` the tile's first
+// column, `chalf` which half of its BLOCK_N columns this warp drains. Waits for the accumulator itself (after
+// requesting the first residual segment).
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& epi, int M, int N, int row, int n0, int b,
+                                              uint32_t tmem_acc, int chalf, uint64_t* full_bar, uint32_t full_phase) {
+  const bool out_f32 = (epi.flags & GEMM_OUT_F32) != 0;
+  const bool do_gelu = (epi.flags & GEMM_GELU) != 0;
+  const bool bias_row = (epi.flags & GEMM_BIAS_ROW) != 0;
+  const bool row_ok = row < M;
+  const int64_t rrow = epi.res_mod > 0 ? (row % epi.res_mod) : row;
+  const float* rptr =
+      (epi.residual && row_ok) ? epi.residual + b * epi.r_batch_stride + rrow * epi.ldr : nullptr;
+  const float row_bias = (bias_row && epi.bias && row_ok) ? epi.bias[row] : 0.0f;
+  constexpr int CHUNKS = BLOCK_N / 32 / 2;  // 32-column chunks per warp (its half of the accumulator)
+  const int c_begin = chalf * CHUNKS;
+  // residual of a full chunk, requested one chunk ahead (the first one before the accumulator is waited for)
+  float4 rv[8];
+  auto load_res = [&](int c, float4 (&dst)[8]) {
+    const int col0 = n0 + c * 32;
+    if (rptr && col0 + 32 <= N) {
+      const float4* rp = reinterpret_cast<const float4*>(rptr + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = rp[j];
+    }
+  };
+  load_res(c_begin, rv);
+
+  mbar_wait(full_bar, full_phase);
+  tc_fence_after();
+
+#pragma unroll 1
+  for (int c = c_begin; c < c_begin + CHUNKS; ++c) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tmem_acc + c * 32,
+                       r);
+    float4 rn[8];
+    if (c + 1 < c_begin + CHUNKS) load_res(c + 1, rn);
+    tmem_ld_wait(r);
+    if (!row_ok) continue;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    const bool full = (col0 + 32 <= N);
+    if (epi.bias) {
+      if (bias_row) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += row_bias;
+      } else if (full) {
+        const float4* bp = reinterpret_cast<const float4*>(epi.bias + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 t = __ldg(bp + j);
+          v[4 * j + 0] += t.x;
+          v[4 * j + 1] += t.y;
+          v[4 * j + 2] += t.z;
+          v[4 * j + 3] += t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) v[j] += epi.bias[col0 + j];
+      }
+    }
+    if (do_gelu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+    }
+    if (rptr) {
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[4 * j + 0] += rv[j].x;
+          v[4 * j + 1] += rv[j].y;
+          v[4 * j + 2] += rv[j].z;
+          v[4 * j + 3] += rv[j].w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) v[j] += rptr[col0 + j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rv[j] = rn[j];
+    if (out_f32) {
+      float* cp = static_cast<float*>(epi.C) + b * epi.c_batch_stride + (int64_t)row * epi.ldc + col0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<float4*>(cp)[j] =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) cp[j] = v[j];
+      }
+    } else {
+      __nv_bfloat16* cp = static_cast<__nv_bfloat16*>(epi.C) + b * epi.c_batch_stride +
+                          (int64_t)row * epi.ldc + col0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+          o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+          o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+          reinterpret_cast<uint4*>(cp)[j] = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) cp[j] = __float2bfloat16_rn(v[j]);
+      }
+    }
+  }
+}
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -171,9 +295,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     // ===================== epilogue warps =====================
     const int q = warp_idx & 3;  // TMEM lane quarter this warp may touch
     const int chalf = (warp_idx - EPI_WARP0) >> 2;  // which half of the accumulator's columns
-    const bool out_f32 = (epi.flags & GEMM_OUT_F32) != 0;
-    const bool do_gelu = (epi.flags & GEMM_GELU) != 0;
-    const bool bias_row = (epi.flags & GEMM_BIAS_ROW) != 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_blk = tile % n_tiles;
@@ -182,117 +303,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
 
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
-      const bool row_ok = row < M;
-      const int64_t rrow = epi.res_mod > 0 ? (row % epi.res_mod) : row;
-      const float* rptr =
-          (epi.residual && row_ok) ? epi.residual + b * epi.r_batch_stride + rrow * epi.ldr : nullptr;
-      const float row_bias = (bias_row && epi.bias && row_ok) ? epi.bias[row] : 0.0f;
-      constexpr int CHUNKS = BLOCK_N / 32 / 2;  // 32-column chunks per warp (its half of the accumulator)
-      const int c_begin = chalf * CHUNKS;
-      // residual of a full chunk, requested one chunk ahead (the first one before the accumulator is waited for)
-      float4 rv[8];
-      auto load_res = [&](int c, float4 (&dst)[8]) {
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        if (rptr && col0 + 32 <= N) {
-          const float4* rp = reinterpret_cast<const float4*>(rptr + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = rp[j];
-        }
-      };
-      load_res(c_begin, rv);
-
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-
-#pragma unroll 1
-      for (int c = c_begin; c < c_begin + CHUNKS; ++c) {
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        if (col0 >= N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + acc * BLOCK_N + c * 32 + (static_cast<uint32_t>(q * 32) << 16),
-                           r);
-        float4 rn[8];
-        if (c + 1 < c_begin + CHUNKS) load_res(c + 1, rn);
-        tmem_ld_wait(r);
-        if (!row_ok) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const bool full = (col0 + 32 <= N);
-        if (epi.bias) {
-          if (bias_row) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += row_bias;
-          } else if (full) {
-            const float4* bp = reinterpret_cast<const float4*>(epi.bias + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 t = __ldg(bp + j);
-              v[4 * j + 0] += t.x;
-              v[4 * j + 1] += t.y;
-              v[4 * j + 2] += t.z;
-              v[4 * j + 3] += t.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) v[j] += epi.bias[col0 + j];
-          }
-        }
-        if (do_gelu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-        }
-        if (rptr) {
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[4 * j + 0] += rv[j].x;
-              v[4 * j + 1] += rv[j].y;
-              v[4 * j + 2] += rv[j].z;
-              v[4 * j + 3] += rv[j].w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) v[j] += rptr[col0 + j];
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rv[j] = rn[j];
-        if (out_f32) {
-          float* cp = static_cast<float*>(epi.C) + b * epi.c_batch_stride + (int64_t)row * epi.ldc + col0;
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(cp)[j] =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) cp[j] = v[j];
-          }
-        } else {
-          __nv_bfloat16* cp = static_cast<__nv_bfloat16*>(epi.C) + b * epi.c_batch_stride +
-                              (int64_t)row * epi.ldc + col0;
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              reinterpret_cast<uint4*>(cp)[j] = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) cp[j] = __float2bfloat16_rn(v[j]);
-          }
-        }
-      }
+      epilogue_tile<BLOCK_N>(epi, M, N, m_blk * BLOCK_M + q * 32 + lane, n_blk * BLOCK_N, b,
+                             tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16), chalf,
+                             &tmem_full_bar[acc], acc_phase);
       // hand the accumulator back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -305,6 +318,202 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
   if (warp_idx == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one 256 x 256 tile per pair of SMs
+// ---------------------------------------------------------------------------
+// The single-CTA kernel above moves (128 + 256) x 64 operand elements into shared memory per k-block and SM, and
+// its main loop is bound by exactly that traffic (TMA writes + operand reads). A CTA pair computes a 256 x 256
+// tile with each CTA holding 128 rows of A and 128 rows of B per k-block - two thirds of the bytes per SM for the
+// same MMA time. CTA 0 of the pair issues the MMAs (tcgen05.mma.cta_group::2 reads both CTAs' shared memory and
+// writes 128 accumulator rows into each CTA's tensor memory); both CTAs load with TMA (completing on CTA 0's
+// barrier), both drain their own half of the accumulator.
+namespace pair {
+constexpr int BN = 256;                      // tile columns (128 rows of B per CTA)
+constexpr int A_BYTES = 128 * BLOCK_K * 2;   // per CTA
+constexpr int B_BYTES = 128 * BLOCK_K * 2;   // per CTA
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int STAGES = 7;  // 7 x 32 KB + barriers = 225.3 KB of the 227 KB
+constexpr int TMEM_COLS = 2 * BN;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a CTA pair: the bytes land in this CTA's shared memory, the transaction completes on `bar_cluster`
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const void* map, uint32_t bar_cluster, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs once all earlier MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+}  // namespace pair
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         EpiParams epi, int M, int N, int K, int batch, int b_batched) {
+  using namespace pair;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // used in CTA 0 only
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // used in CTA 0 only
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_idx = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  const int m_tiles = (M + 255) / 256;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  const int total_tiles = m_tiles * n_tiles * batch;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 2 * EPI_WARPS);  // the epilogue warps of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp_idx == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised, tensor memory allocated in both
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_idx; tile < total_tiles; tile += n_pairs) {
+        const int n_blk = tile % n_tiles;
+        const int m_blk = (tile / n_tiles) % m_tiles;
+        const int b = tile / (n_tiles * m_tiles);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          const uint32_t full0 = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);  // both CTAs' bytes
+          tma_load_3d_pair(sa, &map_a, full0, kb * BLOCK_K, m_blk * 256 + (int)rank * 128, b);
+          tma_load_3d_pair(sb, &map_b, full0, kb * BLOCK_K, n_blk * BN + (int)rank * 128, b_batched ? b : 0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (CTA 0 only) =====================
+    if (rank == 0 && elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair_idx; tile < total_tiles; tile += n_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = make_umma_desc_sw128(sa);
+          const uint64_t bdesc = make_umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_pair(&tmem_full_bar[acc]);  // accumulator complete -> both CTAs' epilogues
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs, own 128 rows each) =====================
+    const int q = warp_idx & 3;
+    const int chalf = (warp_idx - EPI_WARP0) >> 2;
+    int it = 0;
+    for (int tile = pair_idx; tile < total_tiles; tile += n_pairs, ++it) {
+      const int n_blk = tile % n_tiles;
+      const int m_blk = (tile / n_tiles) % m_tiles;
+      const int b = tile / (n_tiles * m_tiles);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      epilogue_tile<BN>(epi, M, N, m_blk * 256 + (int)rank * 128 + q * 32 + lane, n_blk * BN, b,
+                        tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16), chalf, &tmem_full_bar[acc],
+                        acc_phase);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty_bar[acc]), 0));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody touches the peer's shared or tensor memory after this
+  if (warp_idx == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -401,6 +610,36 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+int launch_pair(const GemmArgs& a, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SW_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       pair::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap map_a, map_b;
+  if (make_operand_map(&map_a, a.A, a.K, a.M, a.batch, a.lda, a.a_batch_stride, 128)) return -1;
+  const bool b_batched = a.b_batch_stride != 0 && a.batch > 1;
+  if (make_operand_map(&map_b, a.B, a.K, a.N, b_batched ? a.batch : 1, a.ldb, a.b_batch_stride, 128)) return -1;
+  EpiParams epi;
+  epi.C = a.C;
+  epi.ldc = a.ldc;
+  epi.c_batch_stride = a.c_batch_stride;
+  epi.bias = a.bias;
+  epi.residual = a.residual;
+  epi.ldr = a.ldr;
+  epi.r_batch_stride = a.r_batch_stride;
+  epi.res_mod = a.res_mod;
+  epi.flags = a.flags;
+  const int64_t tiles = (int64_t)((a.M + 255) / 256) * ((a.N + pair::BN - 1) / pair::BN) * a.batch;
+  const int pairs_max = num_sms() / 2;
+  const int grid = 2 * (int)(tiles < pairs_max ? tiles : pairs_max);
+  gemm_tcgen05_pair_kernel<<<grid, NUM_THREADS, pair::SMEM_BYTES, stream>>>(map_a, map_b, epi, a.M, a.N, a.K, a.batch,
+                                                                           b_batched ? 1 : 0);
+  SW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 
 int make_tma_map_2d_bf16(void* map_out, const void* base, int64_t inner, int64_t rows, int64_t ld_elems,
@@ -451,6 +690,12 @@ int gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
     while (bn > 64 && (m_tiles * ((a.N + bn - 1) / bn) * a.batch < num_sms() || a.N <= bn / 2))
       bn >>= 1;
   }
+  // CTA pairs for the large encoder shapes (development switch: SW_GEMM_PAIR=0/1, block_n = 512 forces it)
+  static const int pair_on = [] {
+    const char* e = getenv("SW_GEMM_PAIR");
+    return e ? atoi(e) : 1;
+  }();
+  if (bn == 512 || (pair_on && bn == 256 && a.M >= 2048)) return launch_pair(a, stream);
   switch (bn) {
     case 64: return launch<64>(a, stream);
     case 128: return launch<128>(a, stream);

@@ -74,7 +74,7 @@ def bench(M, N, K, block_n=0, iters=20):
                 cublas_tflops=fl / ms_t / 1e9)
 
 
-def bench_epilogue(M, N, K, flags, bias, res, iters=20):
+def bench_epilogue(M, N, K, flags, bias, res, iters=20, block_n=256):
     """The shapes as the encoder launches them: bias / GELU / f32 residual in and f32 out in the epilogue."""
     A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
     B = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
@@ -82,7 +82,7 @@ def bench_epilogue(M, N, K, flags, bias, res, iters=20):
     C = torch.zeros(M, N, device="cuda", dtype=torch.float32 if out_f32 else torch.bfloat16)
     bias_t = torch.randn(N, device="cuda") if bias else None
     args = (A.data_ptr(), B.data_ptr(), C.data_ptr(), bias_t.data_ptr() if bias else None,
-            C.data_ptr() if res else None, M, N, K, K, K, N, flags, 256, None)  # residual in place, as the engine does
+            C.data_ptr() if res else None, M, N, K, K, K, N, flags, block_n, None)  # residual in place, as the engine does
     for _ in range(3):
         lib.sw_dev_gemm_bf16(*args)
     torch.cuda.synchronize()
@@ -93,7 +93,7 @@ def bench_epilogue(M, N, K, flags, bias, res, iters=20):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    return dict(M=M, N=N, K=K, flags=flags, bias=bias, res=res, ms=ms, tflops=2.0 * M * N * K / ms / 1e9)
+    return dict(M=M, N=N, K=K, flags=flags, bias=bias, res=res, block_n=block_n, ms=ms, tflops=2.0 * M * N * K / ms / 1e9)
 
 
 if __name__ == "__main__":
@@ -117,6 +117,16 @@ if __name__ == "__main__":
         (3000, 1280, 1280, 2, True, True, 256),  # out-projection as the encoder launches it
         (3000, 5120, 1280, 1, True, False, 256),  # FC1: GELU, bf16 out
         (1501, 392, 200, 0, True, True, 0),     # ragged everything, bf16 out with residual
+        # block_n = 512 forces the CTA-pair kernel (256 x 256 tile per two SMs)
+        (256, 256, 64, 2, False, False, 512),
+        (512, 512, 256, 2, False, False, 512),
+        (3000, 1280, 1280, 2, True, True, 512),
+        (3000, 5120, 1280, 1, True, False, 512),
+        (777, 200, 136, 2, True, True, 512),
+        (1501, 392, 200, 0, True, True, 512),
+        (1000, 640, 512, 7, True, True, 512),
+        (96000, 1280, 1280, 0, True, False, 512),
+        (5000, 51866, 384, 2, False, False, 512),
     ]
     allok = True
     for c in cases:
@@ -127,10 +137,15 @@ if __name__ == "__main__":
     if allok:
         for (M, N, K, bn) in [(8192, 8192, 8192, 256), (96000, 1280, 1280, 256), (96000, 5120, 1280, 256),
                               (96000, 1280, 5120, 256), (96000, 3840, 1280, 256), (96000, 1280, 1280, 128),
-                              (1500 * 32, 512, 512, 128), (1500 * 32, 512, 512, 256), (1500*32, 2048, 512, 256)]:
+                              (1500 * 32, 512, 512, 128), (1500 * 32, 512, 512, 256), (1500*32, 2048, 512, 256),
+                              (8192, 8192, 8192, 512), (96000, 1280, 1280, 512), (96000, 5120, 1280, 512),
+                              (96000, 1280, 5120, 512), (96000, 3840, 1280, 512)]:
             print(json.dumps(bench(M, N, K, bn)), flush=True)
         # out-projection (f32 residual stream in place), FC1 (GELU, bf16 out), FC2 (residual), QKV (bias)
-        for (M, N, K, fl, bi, re) in [(96000, 1280, 1280, 2, True, True), (96000, 5120, 1280, 1, True, False),
-                                      (96000, 1280, 5120, 2, True, True), (96000, 3840, 1280, 0, True, False)]:
-            print(json.dumps(bench_epilogue(M, N, K, fl, bi, re)), flush=True)
+        for rep in range(2):
+            for (M, N, K, fl, bi, re) in [(96000, 1280, 1280, 2, True, True), (96000, 5120, 1280, 1, True, False),
+                                          (96000, 1280, 5120, 2, True, True), (96000, 3840, 1280, 0, True, False),
+                                          (96000, 2560, 1280, 0, True, False)]:
+                for bn in (256, 512):  # 512 = CTA pairs
+                    print(json.dumps(bench_epilogue(M, N, K, fl, bi, re, block_n=bn)), flush=True)
     sys.exit(0 if allok else 1)

@@ -1,9 +1,11 @@
 // bf16 x bf16 -> f32 GEMM for sm_100a: TMA -> 128B-swizzled smem ring ->
 // tcgen05.mma (accumulators in TMEM, double buffered) -> tcgen05.ld epilogue.
 //
-// Persistent, warp specialised, one CTA per SM:
-//   warp 0      : TMA producer (one elected lane)
-//   warp 1      : TMEM allocator + MMA issuer (one elected lane)
+// Two kernels share the epilogue: gemm_tcgen05_kernel<64/128/256> (one CTA per 128 x N tile) and
+// gemm_tcgen05_pair_kernel (a CTA pair, cta_group::2, per 256 x 256 tile; used for M >= 2048 with N tiles of 256,
+// see the comment above it). Both are persistent and warp specialised, one CTA per SM:
+//   warp 0      : TMA producer (one thread, chosen by elect.sync)
+//   warp 1      : TMEM allocator + MMA issuer (one thread, chosen by elect.sync)
 //   warps 2..9  : epilogue; warp w drains TMEM lanes [32*(w%4), 32*(w%4)+32) of one column half of the
 //                 accumulator (warps 2-5 the first half, 6-9 the second): eight warps keep twice the loads
 //                 and stores in flight and give every scheduler two warps to alternate between; the residual

@@ -16,8 +16,12 @@
 //                 that global loads and stores leave coalesced (one instruction = 4 rows x 128 B instead of 32
 //                 rows x 16 B). Bit-identical, but SLOWER (12.86 ms; 48 000 x 512 x 512: 375 instead of 544
 //                 TFLOP/s): the main loop is bound by shared-memory traffic (TMA writes + operand reads of a
-//                 128 x 256 tile per SM), and the staging adds to exactly that. The variant is kept as
-//                 tools/dev/gemm_epilogue_staged.cu.txt.
+//                 128 x 256 tile per SM), and the staging adds to exactly that. The same on the CTA-pair kernel
+//                 (where ncu shows l1tex__data_pipe_lsu_wavefronts at 52-67 % of peak in the K = 1280 GEMMs and the
+//                 tensor pipe waiting for a free accumulator 25-65 % of the time): encoder of the 2-layer model
+//                 0.180 ms per window direct, 0.198 staged; FC1 + GELU 1.17 -> 1.78 ms. Variants kept as
+//                 tools/dev/gemm_epilogue_staged.cu.txt and gemm_epilogue_staged_pair.cu.txt. What is left to try
+//                 is a TMA store out of the tile (no LDS / STG in the warps at all).
 //
 // This is the kernel behind every dense contraction of the Whisper path the
 // reference runs through ggml's mul_mat: conv stem (implicit
@@ -62,7 +66,28 @@ struct EpiParams {
   int64_t ldr, r_batch_stride;
   int res_mod;
   int flags;
+  int wide;  // C and residual rows are 32-byte aligned: 256-bit accesses allowed
 };
+
+// 256-bit global accesses (sm_100): a thread of the epilogue owns a row and touches 32 different cache lines per
+// warp instruction, so the LSU cost is per instruction, not per byte - 32 bytes per access halve it.
+__device__ __forceinline__ void ldg256(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6,
+                                       float a7) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3),
+               "f"(a4), "f"(a5), "f"(a6), "f"(a7)
+               : "memory");
+}
+__device__ __forceinline__ void stg256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                       uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+               "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
 
 // Epilogue of one accumulator tile for one warp: `row` is the output row this thread owns (its TMEM lane),
 // `tmem_acc` the accumulator's address with the warp's lane quarter in the upper half, `n0` the tile's first
@@ -86,9 +111,14 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& epi, int M, int N
   auto load_res = [&](int c, float4 (&dst)[8]) {
     const int col0 = n0 + c * 32;
     if (rptr && col0 + 32 <= N) {
-      const float4* rp = reinterpret_cast<const float4*>(rptr + col0);
+      if (epi.wide) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dst[j] = rp[j];
+        for (int j = 0; j < 4; ++j) ldg256(rptr + col0 + 8 * j, dst[2 * j], dst[2 * j + 1]);
+      } else {
+        const float4* rp = reinterpret_cast<const float4*>(rptr + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = rp[j];
+      }
     }
   };
   load_res(c_begin, rv);
@@ -154,7 +184,12 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& epi, int M, int N
     for (int j = 0; j < 8; ++j) rv[j] = rn[j];
     if (out_f32) {
       float* cp = static_cast<float*>(epi.C) + b * epi.c_batch_stride + (int64_t)row * epi.ldc + col0;
-      if (full) {
+      if (full && epi.wide) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          stg256(cp + 8 * j, v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5],
+                 v[8 * j + 6], v[8 * j + 7]);
+      } else if (full) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           reinterpret_cast<float4*>(cp)[j] =
@@ -167,7 +202,15 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& epi, int M, int N
     } else {
       __nv_bfloat16* cp = static_cast<__nv_bfloat16*>(epi.C) + b * epi.c_batch_stride +
                           (int64_t)row * epi.ldc + col0;
-      if (full) {
+      if (full && epi.wide) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          stg256(static_cast<void*>(cp + 16 * j), pack_bf16x2(v[16 * j + 0], v[16 * j + 1]),
+                 pack_bf16x2(v[16 * j + 2], v[16 * j + 3]), pack_bf16x2(v[16 * j + 4], v[16 * j + 5]),
+                 pack_bf16x2(v[16 * j + 6], v[16 * j + 7]), pack_bf16x2(v[16 * j + 8], v[16 * j + 9]),
+                 pack_bf16x2(v[16 * j + 10], v[16 * j + 11]), pack_bf16x2(v[16 * j + 12], v[16 * j + 13]),
+                 pack_bf16x2(v[16 * j + 14], v[16 * j + 15]));
+      } else if (full) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 o;
@@ -566,6 +609,15 @@ int make_operand_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows
   return 0;
 }
 
+// 256-bit epilogue accesses need 32-byte aligned rows of C (and of the residual, when there is one)
+bool epilogue_wide_ok(const GemmArgs& a) {
+  const int64_t esz = (a.flags & GEMM_OUT_F32) ? 4 : 2;
+  bool ok = (reinterpret_cast<uintptr_t>(a.C) & 31) == 0 && (a.ldc * esz) % 32 == 0 && (a.c_batch_stride * esz) % 32 == 0;
+  if (a.residual)
+    ok = ok && (reinterpret_cast<uintptr_t>(a.residual) & 31) == 0 && (a.ldr * 4) % 32 == 0 && (a.r_batch_stride * 4) % 32 == 0;
+  return ok;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -602,6 +654,7 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
   epi.r_batch_stride = a.r_batch_stride;
   epi.res_mod = a.res_mod;
   epi.flags = a.flags;
+  epi.wide = epilogue_wide_ok(a) && !getenv("SW_GEMM_NARROW");
   const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
   const int64_t tiles = (int64_t)m_tiles * n_tiles * a.batch;
@@ -633,6 +686,7 @@ int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   epi.r_batch_stride = a.r_batch_stride;
   epi.res_mod = a.res_mod;
   epi.flags = a.flags;
+  epi.wide = epilogue_wide_ok(a) && !getenv("SW_GEMM_NARROW");
   const int64_t tiles = (int64_t)((a.M + 255) / 256) * ((a.N + pair::BN - 1) / pair::BN) * a.batch;
   const int pairs_max = num_sms() / 2;
   const int grid = 2 * (int)(tiles < pairs_max ? tiles : pairs_max);

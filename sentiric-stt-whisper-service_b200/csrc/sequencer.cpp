@@ -586,7 +586,6 @@ struct Run {
 
   // ---- decode a batch of windows to completion; cross-KV for window index w is already in place
   int decode_windows(std::vector<Window>& wins) {
-    const Vocab& v = m.vocab;
     const int nw = (int)wins.size(), MB = e->max_beams, MR = e->max_rows;
     const int n_max = m.hp.n_text_ctx / 2 - 4;
     pager.reset(e->n_pages, MR, e->h_page_table.p);

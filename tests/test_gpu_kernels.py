@@ -1,0 +1,70 @@
+"""Kernel-level parity of the tcgen05 GEMM family against a plain PyTorch fp32 reference of the same op
+(C = epi(A B^T): bias per column or per row, tanh-GELU, f32 residual, bf16 or f32 out), through the C ABI's
+device-pointer hook sw_dev_gemm_bf16. block_n 64 / 128 / 256 = one CTA per 128 x N tile, 512 = the CTA-pair kernel
+(tcgen05.mma.cta_group::2, 256 x 256 tile per two SMs), 0 = the dispatch the engine uses. Tolerances: 1e-3 of the
+output range for f32 out, 1e-2 for bf16 out (one bf16 rounding of values up to the range)."""
+import importlib.util
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # M, N, K, flags (1 GELU, 2 f32 out, 4 bias per row), bias, residual, block_n
+    (128, 64, 64, 0, False, False, 64),
+    (256, 256, 256, 2, False, False, 0),
+    (1500, 1536, 384, 1, True, False, 0),
+    (1500, 384, 1536, 2, True, True, 0),
+    (777, 200, 136, 2, True, True, 0),        # ragged M / N / K tails
+    (1501, 392, 200, 0, True, True, 128),
+    (1000, 640, 512, 6, True, False, 256),    # row bias
+    (256, 256, 64, 2, False, False, 512),     # one tile of the CTA-pair kernel
+    (3000, 1280, 1280, 2, True, True, 512),   # out-projection as the encoder launches it
+    (3000, 5120, 1280, 1, True, False, 512),  # FC1: GELU, bf16 out
+    (777, 200, 136, 2, True, True, 512),      # ragged, the second CTA of the pair partly / fully out of range
+    (1501, 392, 200, 0, True, True, 512),
+    (1000, 640, 512, 7, True, True, 512),     # row bias + GELU + residual
+    (4096, 2560, 1280, 0, True, False, 0),    # cross-KV shape: the engine's dispatch picks the pair kernel (M >= 2048)
+]
+
+
+@pytest.fixture(scope="module")
+def gemm_check():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    spec = importlib.util.spec_from_file_location("dev_gemm_check", os.path.join(ROOT, "tools", "dev_gemm_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "M%d_N%d_K%d_f%d_bn%d" % (c[0], c[1], c[2], c[3], c[6]))
+def test_tcgen05_gemm_matches_fp32_reference(gemm_check, case):
+    r = gemm_check.run(*case)
+    assert r["ok"], r
+
+
+def test_gemm_is_bit_reproducible_and_pair_equals_single(gemm_check):
+    """Same inputs -> same bits, run to run; and the CTA-pair kernel accumulates in the same order as the
+    single-CTA kernel (k ascending in f32), so both give identical outputs."""
+    import torch
+    lib = gemm_check.lib
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 2304, 1280, 640
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    outs = []
+    for bn in (256, 512, 512, 256):
+        C = torch.empty(M, N, device="cuda", dtype=torch.float32)
+        rc = lib.sw_dev_gemm_bf16(A.data_ptr(), B.data_ptr(), C.data_ptr(), bias.data_ptr(), None, M, N, K, K, K, N,
+                                  2 | 1, bn, None)
+        assert rc == 0, lib.sw_last_error()
+        torch.cuda.synchronize()
+        outs.append(C)
+    assert torch.equal(outs[0], outs[3]) and torch.equal(outs[1], outs[2])
+    assert torch.equal(outs[0], outs[1])

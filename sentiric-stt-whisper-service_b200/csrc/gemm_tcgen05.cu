@@ -609,8 +609,11 @@ int make_operand_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows
   return 0;
 }
 
-// 256-bit epilogue accesses need 32-byte aligned rows of C (and of the residual, when there is one)
+// 256-bit epilogue accesses need 32-byte aligned rows of C (and of the residual, when there is one);
+// development switch: SW_GEMM_NARROW=1 keeps the 128-bit accesses
 bool epilogue_wide_ok(const GemmArgs& a) {
+  static const bool narrow = getenv("SW_GEMM_NARROW") != nullptr;
+  if (narrow) return false;
   const int64_t esz = (a.flags & GEMM_OUT_F32) ? 4 : 2;
   bool ok = (reinterpret_cast<uintptr_t>(a.C) & 31) == 0 && (a.ldc * esz) % 32 == 0 && (a.c_batch_stride * esz) % 32 == 0;
   if (a.residual)
@@ -654,7 +657,7 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
   epi.r_batch_stride = a.r_batch_stride;
   epi.res_mod = a.res_mod;
   epi.flags = a.flags;
-  epi.wide = epilogue_wide_ok(a) && !getenv("SW_GEMM_NARROW");
+  epi.wide = epilogue_wide_ok(a);
   const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
   const int64_t tiles = (int64_t)m_tiles * n_tiles * a.batch;
@@ -686,7 +689,7 @@ int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   epi.r_batch_stride = a.r_batch_stride;
   epi.res_mod = a.res_mod;
   epi.flags = a.flags;
-  epi.wide = epilogue_wide_ok(a) && !getenv("SW_GEMM_NARROW");
+  epi.wide = epilogue_wide_ok(a);
   const int64_t tiles = (int64_t)((a.M + 255) / 256) * ((a.N + pair::BN - 1) / pair::BN) * a.batch;
   const int pairs_max = num_sms() / 2;
   const int grid = 2 * (int)(tiles < pairs_max ? tiles : pairs_max);

@@ -82,3 +82,27 @@ def test_product_path_never_touches_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", "Makefile")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "whisper_oracle" not in txt and "oracle/" not in txt and "from oracle" not in txt, f
+
+
+def test_issuing_threads_are_elected_not_lane_tested(swb):
+    """Regression guard for a performance bug found in SASS ('elect.sync'): a TMA producer or MMA issuer
+    written as `if (lane == 0)` makes ptxas wrap every UTMALDG / UTCHMMA in a loop over the active lanes
+    (R2UR ... ELECT ... BRA.U.ANY, ~110 cycles per instruction). With elect.sync the built objects contain the
+    tensor-core / TMA instructions and none of those loops."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    build = os.path.join(ROOT, "sentiric-stt-whisper-service_b200", "build")
+    want = {"gemm_tcgen05.o": ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG"), "attn_enc_tc.o": ("UTCHMMA", "UTMALDG"),
+            "skinny_gemm.o": ("UTMALDG",), "xattn.o": ("UTMALDG",)}
+    for obj, mnemonics in want.items():
+        path = os.path.join(build, obj)
+        if not os.path.exists(path):
+            pytest.skip("objects not built in-tree (%s)" % obj)
+        sass = subprocess.run([cuobjdump, "-sass", path], capture_output=True, text=True, timeout=300).stdout
+        for m in mnemonics:
+            assert m in sass, (obj, m)
+        assert sass.count("BRA.U.ANY") == 0, "%s: %d lane loops around uniform-datapath instructions" % (
+            obj, sass.count("BRA.U.ANY"))

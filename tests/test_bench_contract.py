@@ -35,3 +35,17 @@ def test_bench_names_the_baseline_metric_and_never_imports_the_oracle_on_the_gpu
             ctx = "\n".join(src.splitlines()[max(0, i - 12):i])
             assert "def run_reference" in src[:src.index(line)] and (
                 "no_cpu_baseline" in ctx or "run_reference" in ctx or "cpu_baseline" in ctx or "impl = pro" in ctx), line
+
+
+def test_our_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback on the measured path: without a CUDA device bench.py's own arm exits with an error and
+    prints no JSON line (the reference arm is the only thing that runs on host cores)."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--model", "micro", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode != 0
+    assert "no CPU fallback" in (r.stdout + r.stderr)
+    assert not [l for l in r.stdout.splitlines() if l.startswith("{")]

@@ -242,7 +242,7 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
       }
-      // ---- pass 2: P = exp2(S * sc - m) -> bf16 -> shared memory (the A operand of P V)
+      // ---- pass 2: P = exp2(S * sc - m) -> bf16 -> tensor memory (the A operand of P V, TS form)
       float lsum = 0.f;
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {

@@ -45,7 +45,9 @@ SW_API void sw_log_set(sw_log_callback cb, void* user);
 typedef struct sw_ctx_params {
   int device;          /* CUDA ordinal */
   int max_batch;       /* windows decoded together (default 64) */
-  int max_beams;       /* decoders per window (default 5) */
+  int max_beams;       /* sizes the row budget: max_batch * max_beams decoder rows per step (default 5). Any request
+                          may still use up to 8 decoders per window (WHISPER_MAX_DECODERS); it then gets fewer
+                          windows per device pass */
   int flash_attn;      /* accepted for API compatibility; always fused */
   int n_lanes;         /* independent batches in flight on the device (each lane has its own KV caches,
                         * activations and stream; the weights are shared). A decoder step is a chain of

@@ -187,12 +187,8 @@ int encoder_attention(const bf16* qkv, bf16* out, int n_win, int T, int d, int n
                       cudaStream_t stream) {
   if (n_win <= 0) return 0;
   SW_CHECK(d == n_head * DH, "encoder_attention: head dim must be 64 (d=%d heads=%d)", d, n_head);
-  static bool attr = false;
-  if (!attr) {
-    SW_CUDA_CHECK(cudaFuncSetAttribute(encoder_attention_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    attr = true;
-  }
+  static SmemOptIn opt_in;  // per device (host_common.h)
+  SW_CUDA_CHECK(opt_in.ensure(encoder_attention_kernel, ATT_SMEM));
   dim3 grid((T + BQ - 1) / BQ, n_head, n_win);
   encoder_attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(qkv, out, T, d);
   SW_CUDA_CHECK(cudaGetLastError());

@@ -322,11 +322,8 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
 int encoder_attention_tc(const bf16* qkv, bf16* out, int n_win, int T, int d, int n_head, cudaStream_t stream) {
   if (n_win <= 0) return 0;
   SW_CHECK(d == n_head * DH, "encoder_attention: head dim must be 64 (d=%d heads=%d)", d, n_head);
-  static bool attr = false;
-  if (!attr) {
-    SW_CUDA_CHECK(cudaFuncSetAttribute(encoder_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    attr = true;
-  }
+  static SmemOptIn opt_in;  // per device (host_common.h)
+  SW_CUDA_CHECK(opt_in.ensure(encoder_attention_tc_kernel, ATT_SMEM));
   CUtensorMap map;
   if (make_tma_map_2d_bf16(&map, qkv, 3 * (int64_t)d, (int64_t)n_win * T, 3 * (int64_t)d, 64, 128)) return -1;
   dim3 grid((T + TQ - 1) / TQ, n_head, n_win);

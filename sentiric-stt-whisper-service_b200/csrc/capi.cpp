@@ -86,8 +86,8 @@ void sw_ctx_destroy(sw_ctx* ctx) {
   if (ctx->e) {
     cudaSetDevice(ctx->e->device);
     cudaDeviceSynchronize();
-    sw::prosody_state_free(ctx->prosody);
-    sw::resample_state_free(ctx->resample);
+    sw::prosody_state_free(ctx->prosody.load());
+    sw::resample_state_free(ctx->resample.load());
     for (Engine* l : ctx->lanes) delete l;
     delete ctx->e;
   }

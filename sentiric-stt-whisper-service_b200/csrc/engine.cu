@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <tuple>
 
@@ -53,7 +54,7 @@ static int engine_init(Engine* e, const char* path, const sw_ctx_params* p, cons
   e->max_batch = (p && p->max_batch > 0) ? p->max_batch : 64;
   e->max_beams = (p && p->max_beams > 0) ? p->max_beams : 5;
   SW_CHECK(e->max_beams <= 8, "max_beams %d > 8", e->max_beams);
-  e->max_rows = e->max_batch * e->max_beams;
+  e->max_rows = std::max(8, e->max_batch * e->max_beams);  // any single window may run 8 decoders
   {
     const char* a = getenv("SW_ATTN");  // development switch: SW_ATTN=legacy selects the mma.sync kernel
     e->legacy_attention = a && strcmp(a, "legacy") == 0;
@@ -333,11 +334,16 @@ static int enqueue_decode_step(Engine* e, int R, int n_groups, int max_count, bo
   return 0;
 }
 
+// Everything that shapes the captured launch sequence OR is passed to a kernel BY VALUE: a graph replays
+// the arguments it was captured with, so the by-value members of LogitCfg (sw_full_params.suppress_blank,
+// .max_initial_ts) are part of the key. Pointers (d_suppress, the row descriptors) are fixed per lane and
+// their contents are refreshed per run / per step.
 struct StepKey {
-  int R, G, max_count, want_logits, n_lrows, upload_pt, timing;
+  int R, G, max_count, want_logits, n_lrows, upload_pt, timing, suppress_blank, max_initial_ts_id;
   bool operator<(const StepKey& o) const {
-    return std::tie(R, G, max_count, want_logits, n_lrows, upload_pt, timing) <
-           std::tie(o.R, o.G, o.max_count, o.want_logits, o.n_lrows, o.upload_pt, o.timing);
+    return std::tie(R, G, max_count, want_logits, n_lrows, upload_pt, timing, suppress_blank, max_initial_ts_id) <
+           std::tie(o.R, o.G, o.max_count, o.want_logits, o.n_lrows, o.upload_pt, o.timing, o.suppress_blank,
+                    o.max_initial_ts_id);
   }
 };
 struct StepGraph {
@@ -377,7 +383,8 @@ int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_
     // it (one host call per step instead of ~460, and no inter-kernel launch gaps).
     if (!e->step_graphs) e->step_graphs = new StepGraphCache();
     StepGraphCache& cache = *static_cast<StepGraphCache*>(e->step_graphs);
-    const StepKey key{R, n_groups, max_count, want_logits ? 1 : 0, n_lrows, 0, e->kernel_timing ? 1 : 0};
+    const StepKey key{R, n_groups, max_count, want_logits ? 1 : 0, n_lrows, 0, e->kernel_timing ? 1 : 0,
+                      cfg.suppress_blank, cfg.max_initial_ts_id};
     auto it = cache.graphs.find(key);
     if (it == cache.graphs.end()) {
       if (cache.graphs.size() > 512) {  // bounded: drop everything and start over

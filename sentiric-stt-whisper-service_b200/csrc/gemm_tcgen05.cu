@@ -621,26 +621,13 @@ bool epilogue_wide_ok(const GemmArgs& a) {
   return ok;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms() { return device_sm_count(); }  // of the current device (host_common.h)
 
 template <int BLOCK_N>
 int launch(const GemmArgs& a, cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SW_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  static SmemOptIn opt_in;  // per device (host_common.h)
+  SW_CUDA_CHECK(opt_in.ensure(gemm_tcgen05_kernel<BLOCK_N>, C::SMEM_BYTES));
   CUtensorMap map_a, map_b;
   if (make_operand_map(&map_a, a.A, a.K, a.M, a.batch, a.lda, a.a_batch_stride, BLOCK_M)) return -1;
   const bool b_batched = a.b_batch_stride != 0 && a.batch > 1;
@@ -669,12 +656,8 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
 }
 
 int launch_pair(const GemmArgs& a, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    SW_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       pair::SMEM_BYTES));
-    attr_set = true;
-  }
+  static SmemOptIn opt_in;
+  SW_CUDA_CHECK(opt_in.ensure(gemm_tcgen05_pair_kernel, pair::SMEM_BYTES));
   CUtensorMap map_a, map_b;
   if (make_operand_map(&map_a, a.A, a.K, a.M, a.batch, a.lda, a.a_batch_stride, 128)) return -1;
   const bool b_batched = a.b_batch_stride != 0 && a.batch > 1;

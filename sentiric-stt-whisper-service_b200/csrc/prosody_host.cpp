@@ -86,19 +86,19 @@ int run(sw_ctx* ctx, const void* pcm, int is_f32, int64_t n_samples, int sample_
   sw_prosody_opts o = opts ? *opts : sw_prosody_default_opts();
   SW_CHECK(o.lpf_alpha > 0.0f && o.lpf_alpha <= 1.0f, "prosody: lpf_alpha %g outside (0, 1]", o.lpf_alpha);
   SW_CUDA_CHECK(cudaSetDevice(ctx->e->device));
-  if (!ctx->prosody) {
-    std::lock_guard<std::mutex> lk(ctx->e->mu);
-    if (!ctx->prosody) {
+  if (!ctx->prosody.load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lk(ctx->aux_mu);
+    if (!ctx->prosody.load(std::memory_order_relaxed)) {
       ProsodyState* st = new ProsodyState();
       if (cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete st;
         set_last_error("prosody: cannot create a stream");
         return -1;
       }
-      ctx->prosody = st;
+      ctx->prosody.store(st, std::memory_order_release);
     }
   }
-  ProsodyState& st = *static_cast<ProsodyState*>(ctx->prosody);
+  ProsodyState& st = *static_cast<ProsodyState*>(ctx->prosody.load(std::memory_order_acquire));
   std::lock_guard<std::mutex> lk(st.mu);
   const int shift = sample_rate / 100;
   std::vector<ProsodySeg> segs;

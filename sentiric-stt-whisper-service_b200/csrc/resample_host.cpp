@@ -59,9 +59,9 @@ int sw_resample_f32(sw_ctx* ctx, const float* in, int64_t n_in, int sr_in, int s
   SW_CHECK(sr_in >= 1000 && sr_in <= 768000 && sr_out >= 1000 && sr_out <= 768000, "resample: rates %d -> %d", sr_in,
            sr_out);
   SW_CUDA_CHECK(cudaSetDevice(ctx->e->device));
-  if (!ctx->resample) {
-    std::lock_guard<std::mutex> lk(ctx->e->mu);
-    if (!ctx->resample) {
+  if (!ctx->resample.load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lk(ctx->aux_mu);
+    if (!ctx->resample.load(std::memory_order_relaxed)) {
       ResampleState* st = new ResampleState();
       std::vector<float> table;
       build_table(table);
@@ -71,10 +71,10 @@ int sw_resample_f32(sw_ctx* ctx, const float* in, int64_t n_in, int sr_in, int s
         set_last_error("resample: cannot set up the device state");
         return -1;
       }
-      ctx->resample = st;
+      ctx->resample.store(st, std::memory_order_release);
     }
   }
-  ResampleState& st = *static_cast<ResampleState*>(ctx->resample);
+  ResampleState& st = *static_cast<ResampleState*>(ctx->resample.load(std::memory_order_acquire));
   std::lock_guard<std::mutex> lk(st.mu);
   const int64_t n_out = sw_resample_out_len(n_in, sr_in, sr_out);
   if (n_out <= 0) return 0;

@@ -586,10 +586,14 @@ struct Run {
 
   // ---- decode a batch of windows to completion; cross-KV for window index w is already in place
   int decode_windows(std::vector<Window>& wins) {
-    const int nw = (int)wins.size(), MB = e->max_beams, MR = e->max_rows;
+    const int nw = (int)wins.size(), MR = e->max_rows;
+    // self-KV slots: window w owns slots [slot_base[w], slot_base[w] + n_cur) - the batch was admitted with
+    // sum(n_cur) <= MR rows, so every slot index stays below the page table's MR rows
+    std::vector<int> slot_base(nw, 0);
+    for (int w = 1; w < nw; ++w) slot_base[w] = slot_base[w - 1] + wins[w - 1].n_cur;
     const int n_max = m.hp.n_text_ctx / 2 - 4;
     pager.reset(e->n_pages, MR, e->h_page_table.p);
-    auto slot_of = [&](int w, int j) { return w * MB + j; };
+    auto slot_of = [&](int w, int j) { return slot_base[w] + j; };
 
     // ---- prompts, position by position (only decoder 0 of each window)
     int max_prompt = 0;
@@ -1013,9 +1017,12 @@ struct Run {
     beam = p.strategy == 1 ? std::max(1, p.beam_size) : 1;
     best_of = std::max(1, p.best_of);
     if (p.strategy == 1) best_of = std::max(1, p.best_of);  // upstream: used when falling back to t > 0
-    SW_CHECK(beam <= e->max_beams, "beam_size %d exceeds the context's max_beams %d", beam, e->max_beams);
+    // whisper.cpp allows WHISPER_MAX_DECODERS = 8 decoders per window whatever the context was created with;
+    // sw_ctx_params.max_beams only sizes the row budget (max_batch * max_beams rows per step): a request with more
+    // decoders per window than that runs with fewer windows per device pass
+    SW_CHECK(beam <= 8, "beam_size %d exceeds the 8 decoders per window whisper.cpp allows", beam);
     if (p.temperature_inc > 0.0f || p.temperature > 0.0f)
-      SW_CHECK(best_of <= e->max_beams, "best_of %d exceeds the context's max_beams %d", best_of, e->max_beams);
+      SW_CHECK(best_of <= 8, "best_of %d exceeds the 8 decoders per window whisper.cpp allows", best_of);
     if (p.temperature_inc > 0.0f)
       for (float t = p.temperature; t < 1.0f + 1e-6f; t += p.temperature_inc) temps.push_back(t);
     else

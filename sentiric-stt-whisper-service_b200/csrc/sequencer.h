@@ -1,5 +1,7 @@
 // Result containers behind the C ABI and the batched whisper_full_with_state entry point.
 #pragma once
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -8,8 +10,11 @@
 struct sw_ctx {
   sw::Engine* e = nullptr;            // lane 0: owns the model; the stage hooks run here
   std::vector<sw::Engine*> lanes;     // further lanes: own buffers and stream, weights shared with e
-  void* prosody = nullptr;            // sw::ProsodyState (prosody_host.cpp), created on first use
-  void* resample = nullptr;           // sw::ResampleState (resample_host.cpp), created on first use
+  // side states, created on first use under aux_mu (never under Engine::mu, which a running transcription
+  // batch holds for its whole duration): sw::ProsodyState (prosody_host.cpp), sw::ResampleState (resample_host.cpp)
+  std::mutex aux_mu;
+  std::atomic<void*> prosody{nullptr};
+  std::atomic<void*> resample{nullptr};
 };
 struct sw_segment {
   int64_t t0 = 0, t1 = 0;

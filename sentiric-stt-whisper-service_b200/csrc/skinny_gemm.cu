@@ -227,12 +227,9 @@ int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, cons
   SW_CHECK(partial || out, "skinny_gemm: null output");
   SW_CHECK((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
            "skinny_gemm: operands must be 16-byte aligned");
-  static bool attr = false;
-  if (!attr) {
-    SW_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<32>::SMEM));
-    SW_CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<40>::SMEM));
-    attr = true;
-  }
+  static SmemOptIn opt_in32, opt_in40;  // per device (host_common.h)
+  SW_CUDA_CHECK(opt_in32.ensure(skinny_gemm_kernel<32>, SkCfg<32>::SMEM));
+  SW_CUDA_CHECK(opt_in40.ensure(skinny_gemm_kernel<40>, SkCfg<40>::SMEM));
   const int k_slice = K / split;
   const int row_blocks = (R + SK_BM - 1) / SK_BM;
   static const int force_bn = getenv("SW_SKINNY_BN") ? atoi(getenv("SW_SKINNY_BN")) : 0;  // development switch

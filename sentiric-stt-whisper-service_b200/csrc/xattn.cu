@@ -269,12 +269,7 @@ cross_combine_kernel(const float* __restrict__ ws, int n_chunks, int d, int n_he
   reinterpret_cast<uint4*>(out + (int64_t)r * d)[c] = o;
 }
 
-int xa_num_sms() {
-  int sms = 148, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sms > 0 ? sms : 148;
-}
+int xa_num_sms() { return device_sm_count(); }  // of the current device, cached per ordinal (host_common.h)
 
 // stages per work item: the value that leaves the fewest idle SM-slots in the last wave
 void xa_plan(int n_groups, int T, int d, int max_ctas, int* spc_out, int* n_chunks, int* n_stages, int* grid) {
@@ -340,12 +335,8 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
   const int threads = (n_cons + 1) * 32;
 #define XA_LAUNCH(H)                                                                                  \
   do {                                                                                                \
-    static int attr_smem = 0;                                                                         \
-    if (attr_smem < (int)smem) {                                                                      \
-      SW_CUDA_CHECK(cudaFuncSetAttribute(cross_attention_kernel<H>,                                   \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-      attr_smem = (int)smem;                                                                          \
-    }                                                                                                 \
+    static SmemOptIn opt_in; /* per device (host_common.h) */                                         \
+    SW_CUDA_CHECK(opt_in.ensure(cross_attention_kernel<H>, (int)smem));                               \
     SW_CUDA_CHECK(launch_pdl(cross_attention_kernel<H>, dim3(grid), dim3(threads), smem, stream, map, \
                              q, d_grp_win, d_grp_start, d_grp_count, T, d, n_head, n_cons, spc,        \
                              n_stages, n_chunks, n_items, ws, 0u));                                    \

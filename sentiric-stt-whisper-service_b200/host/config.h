@@ -59,4 +59,6 @@ struct Settings {
   int gpu_device = 0;        // CUDA ordinal of this replica (one engine per GPU)
   int max_batch = 64;        // 30 s windows decoded together
   int batch_window_us = 300; // how long the dispatcher waits for more concurrent callers
+  int admission_slots = 0;   // callers admitted at once (the reference's state pool size); 0 = auto:
+                             // max(parallel_requests, 2 * max_batch), so that the defaults can fill a device pass
 };

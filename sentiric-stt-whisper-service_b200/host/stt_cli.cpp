@@ -6,7 +6,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <math.h>
+
+#include <atomic>
+#include <chrono>
 #include <fstream>
+#include <map>
 #include <thread>
 
 #include "stream_session.h"
@@ -34,15 +39,45 @@ int main(int argc, char** argv) {
     fprintf(stderr, "usage: %s <model_dir> <model_file> <pcm16.raw> [n_concurrent] [beam] [stream|batch] [sample_rate]\n", argv[0]);
     return 2;
   }
+  // trailing key=value arguments (any position after the raw file): split them off the positional ones
+  std::map<std::string, std::string> kv;
+  {
+    int w = 1;
+    for (int i = 1; i < argc; ++i) {
+      const char* eq = i >= 4 ? strchr(argv[i], '=') : nullptr;
+      if (eq) kv[std::string(argv[i], eq - argv[i])] = eq + 1;
+      else argv[w++] = argv[i];
+    }
+    argc = w;
+  }
+  auto opt = [&](const char* k, int def) { return kv.count(k) ? atoi(kv[k].c_str()) : def; };
   Settings s;
   s.model_dir = argv[1];
   s.model_filename = argv[2];
   const int n_conc = argc > 4 ? atoi(argv[4]) : 1;
   s.beam_size = argc > 5 ? atoi(argv[5]) : 1;
-  s.language = "en";
+  s.language = kv.count("language") ? kv["language"] : "en";
   s.parallel_requests = std::max(1, n_conc);
-  s.max_batch = 8;
-  s.batch_window_us = 20000;
+  s.max_batch = opt("max_batch", 8);
+  s.batch_window_us = opt("batch_window_us", 20000);
+  s.admission_slots = opt("admission", 0);
+  s.request_queue_timeout_ms = opt("timeout_ms", s.request_queue_timeout_ms);
+  s.n_threads = opt("n_threads", s.n_threads);
+  s.gpu_device = opt("device", 0);
+  s.enable_vad = opt("enable_vad", 0) != 0;  // the tests run without the gate unless they ask for it
+  RequestOptions ropt;
+  ropt.beam_size = opt("req_beam", -1);
+  ropt.best_of = opt("req_best_of", -1);
+  if (kv.count("req_temperature")) ropt.temperature = (float)atof(kv["req_temperature"].c_str());
+  // vad=energy: a stand-in gate for the hook (mean |x| above 1e-3 = speech); the reference's Silero model is not here
+  auto install_vad = [&](SttEngine& e) {
+    if (kv.count("vad") && kv["vad"] == "energy")
+      e.set_vad_fn([](const float* x, size_t n) {
+        double a = 0;
+        for (size_t i = 0; i < n; ++i) a += fabs(x[i]);
+        return n > 0 && a / n > 1e-3;
+      });
+  };
   std::ifstream f(argv[3], std::ios::binary);
   std::vector<char> raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
   std::vector<int16_t> pcm(raw.size() / 2);
@@ -54,6 +89,7 @@ int main(int argc, char** argv) {
     // 0.5 s chunks and closed with an empty chunk: their re-transcriptions meet in the dispatcher
     try {
       SttEngine engine(s);
+      install_vad(engine);
       std::vector<std::string> finals(n_conc);
       std::vector<int> partials(n_conc, 0), calls(n_conc, 0);
       std::vector<std::thread> th;
@@ -87,17 +123,76 @@ int main(int argc, char** argv) {
       return 1;
     }
   }
+  const std::string mode = argc > 6 ? argv[6] : "batch";
+  if (mode == "bench") {
+    // The reference-facing front door under load: n_conc caller threads, each handing its own 30 s clip to
+    // SttEngine::transcribe_pcm16 as a pageable std::vector (what the HTTP / gRPC handlers do), `steps` timed
+    // rounds after `warmup` untimed ones. The raw file holds the clips back to back (clip=<samples per clip>).
+    try {
+      const size_t clip = (size_t)opt("clip", 480000);
+      const int n_clips = std::max<int>(1, (int)(pcm.size() / clip));
+      const int steps = opt("steps", 3), warmup = opt("warmup", 1);
+      SttEngine engine(s);
+      install_vad(engine);
+      std::vector<std::vector<int16_t>> clips(n_conc);
+      for (int i = 0; i < n_conc; ++i) {
+        const size_t off = (size_t)(i % n_clips) * clip;
+        clips[i].assign(pcm.begin() + off, pcm.begin() + std::min(pcm.size(), off + clip));
+      }
+      std::atomic<long> tokens{0}, segments{0}, failures{0};
+      auto round = [&] {
+        std::vector<std::thread> th;
+        for (int i = 0; i < n_conc; ++i)
+          th.emplace_back([&, i] {
+            SttEngine::PerformanceMetrics m{};
+            try {
+              auto r = engine.transcribe_pcm16(clips[i], sample_rate, ropt, &m);
+              tokens += m.token_count;
+              segments += (long)r.size();
+            } catch (const std::exception&) {
+              ++failures;
+            }
+          });
+        for (auto& t : th) t.join();
+      };
+      for (int k = 0; k < warmup; ++k) round();
+      tokens = 0; segments = 0;
+      const long b0 = engine.batches_run();
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int k = 0; k < steps; ++k) round();
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      double audio_s = 0;
+      for (auto& c : clips) audio_s += (double)c.size() / sample_rate;
+      printf("{\"mode\": \"bench\", \"callers\": %d, \"steps\": %d, \"seconds\": %.6f, \"audio_s_per_s\": %.3f, "
+             "\"ms_per_step\": %.3f, \"tokens\": %ld, \"segments\": %ld, \"failures\": %ld, \"device_passes\": %ld, "
+             "\"beam\": %d, \"language\": \"%s\"}\n",
+             n_conc, steps, dt, audio_s * steps / dt, 1e3 * dt / steps, tokens.load(), segments.load(), failures.load(),
+             engine.batches_run() - b0, ropt.beam_size >= 0 ? ropt.beam_size : s.beam_size, s.language.c_str());
+      return 0;
+    } catch (const std::exception& e) {
+      fprintf(stderr, "error: %s\n", e.what());
+      return 1;
+    }
+  }
   try {
     SttEngine engine(s);
+    install_vad(engine);
     std::vector<std::vector<TranscriptionResult>> out(n_conc);
     std::vector<SttEngine::PerformanceMetrics> met(n_conc);
+    std::vector<int> busy(n_conc, 0);
     std::vector<std::thread> th;
     for (int i = 0; i < n_conc; ++i)
-      th.emplace_back([&, i] { out[i] = engine.transcribe_pcm16(pcm, sample_rate, RequestOptions(), &met[i]); });
+      th.emplace_back([&, i] {
+        try {
+          out[i] = engine.transcribe_pcm16(pcm, sample_rate, ropt, &met[i]);
+        } catch (const EngineBusyException& ex) {  // stt_engine.cpp:70-74
+          busy[i] = std::string(ex.what()) == "Server is busy (Queue timeout)" ? 1 : -1;
+        }
+      });
     for (auto& t : th) t.join();
     for (int i = 0; i < n_conc; ++i) {
-      printf("{\"request\": %d, \"token_count\": %d, \"batches_run\": %ld, \"segments\": [", i, met[i].token_count,
-             engine.batches_run());
+      printf("{\"request\": %d, \"busy\": %d, \"token_count\": %d, \"batches_run\": %ld, \"segments\": [", i, busy[i],
+             met[i].token_count, engine.batches_run());
       for (size_t k = 0; k < out[i].size(); ++k) {
         const TranscriptionResult& r = out[i][k];
         printf("%s{\"t0\": %lld, \"t1\": %lld, \"prob\": %.6f, \"language\": \"%s\", \"speaker\": \"%s\", \"text\": \"%s\", ",

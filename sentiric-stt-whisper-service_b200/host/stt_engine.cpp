@@ -45,15 +45,34 @@ static int abort_trampoline(void* user) {  // stt_engine.cpp:17-23
 SttEngine::SttEngine(const Settings& settings) : settings_(settings) {
   // :26-34 - load the model or throw
   const std::string model_path = settings_.model_dir + "/" + settings_.model_filename;
+  // row budget of the context: max_batch windows x the configured decoders per window. A request may still ask
+  // for up to 8 decoders (RequestOptions.beam_size / best_of; whisper.cpp's WHISPER_MAX_DECODERS) - such a pass
+  // then carries fewer windows (sw_ctx_params.max_beams)
   const int max_beams = std::max(1, std::min(8, std::max(settings_.beam_size, settings_.best_of)));
   ctx_ = ModelManager::load_to_device(settings_, model_path, max_beams);
   if (!ctx_) {
     fprintf(stderr, "[stt_engine] %s\n", sw_last_error());
     throw std::runtime_error("Whisper model initialization failed");
   }
-  // :36-42 - the state pool becomes an admission counter
-  free_slots_ = std::max(1, settings_.parallel_requests);
-  // :44-52 - Silero VAD is a CPU-side pre-gate outside the hot path: not loaded
+  // :36-42 - the state pool becomes an admission counter. The reference sizes it with parallel_requests
+  // (default 2: one whisper_state each, decoded one by one); here a device pass decodes max_batch windows
+  // together, so admitting only 2 callers would starve it. admission_slots (0 = auto) decouples the two:
+  // auto admits max(parallel_requests, 2 * max_batch) callers; the bounded wait and EngineBusyException stay.
+  free_slots_ = settings_.admission_slots > 0
+                    ? settings_.admission_slots
+                    : std::max(std::max(1, settings_.parallel_requests), 2 * std::max(1, settings_.max_batch));
+  // :44-52 - the reference loads a Silero model into whisper.cpp's CPU VAD. Not part of this build (see
+  // set_vad_fn in the header): say so instead of silently running without the gate.
+  if (settings_.enable_vad) {
+    const std::string vad_path = settings_.model_dir + "/" + settings_.vad_model_filename;
+    FILE* f = fopen(vad_path.c_str(), "rb");
+    if (f) fclose(f);
+    fprintf(stderr,
+            "[stt_engine] WARNING: enable_vad is set but this engine has no Silero evaluator (%s %s). The speech "
+            "pre-gate stays OPEN, as in the reference when whisper_vad_init_from_file_with_params fails, until "
+            "SttEngine::set_vad_fn() installs one; silence is decoded by Whisper and filtered by no_speech_thold.\n",
+            vad_path.c_str(), f ? "is present but cannot be evaluated" : "is missing");
+  }
   dispatcher_ = std::thread([this] { dispatcher_loop(); });
 }
 
@@ -134,8 +153,10 @@ void SttEngine::dispatcher_loop() {
         r->error = err;
         r->result = res[i];
         r->done = true;
+        // notify while holding r->m: the Request lives on the waiter's stack, and a waiter that saw done == true
+        // after an unlock-then-notify could return and destroy the condition variable under notify_one()
+        r->cv.notify_one();
       }
-      r->cv.notify_one();
     }
   }
 }
@@ -187,8 +208,40 @@ std::vector<TranscriptionResult> SttEngine::run_request(const float* pcm, size_t
     }
     return {};
   }
-  // :169-194 - the Silero VAD pre-gate is not part of this build (see constructor); enable_vad is
-  // honoured as "no gate", which is also what the deployment runs with.
+  // :169-194 - speech pre-gate (hook, see set_vad_fn): no speech -> the reference's placeholder result
+  if (settings_.enable_vad && vad_fn_) {
+    bool speech;
+    {
+      std::vector<float> tmp;
+      const float* f = pcm;
+      if (!f) {  // int16 caller: the gate sees what the reference's /32768 loop (:117-125) would hand it
+        tmp.resize(pcm_size);
+        for (size_t i = 0; i < pcm_size; ++i) tmp[i] = static_cast<float>(pcm16[i]) / 32768.0f;
+        f = tmp.data();
+      }
+      std::lock_guard<std::mutex> lk(vad_mutex_);  // :110
+      speech = vad_fn_(f, pcm_size);
+    }
+    if (!speech) {
+      TranscriptionResult empty_res{};
+      empty_res.text = "";
+      empty_res.language = "unknown";
+      empty_res.prob = 0.0f;
+      empty_res.t0 = 0;
+      empty_res.t1 = static_cast<int64_t>(pcm_size / 16.0);
+      empty_res.speaker_turn_next = false;
+      empty_res.token_count = 0;
+      empty_res.affective = prosody_fn_ ? prosody_fn_(nullptr, 0, 16000, options.prosody_opts)
+                                        : neutral_prosody(nullptr, 0, 16000, options.prosody_opts);
+      empty_res.speaker_id = "unknown";
+      if (out_metrics) {
+        out_metrics->queue_time_ms = 0;
+        out_metrics->processing_time_ms = std::chrono::duration<double, std::milli>(Clock::now() - t_start).count();
+        out_metrics->token_count = 0;
+      }
+      return {empty_res};
+    }
+  }
 
   acquire_slot();  // throws EngineBusyException after request_queue_timeout_ms (:197-198)
   struct SlotGuard {

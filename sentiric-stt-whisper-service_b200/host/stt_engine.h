@@ -83,6 +83,15 @@ class SttEngine {
 
   // B200 additions
   void set_prosody_fn(ProsodyFn fn) { prosody_fn_ = std::move(fn); }
+  // Speech pre-gate of stt_engine.cpp:108-115,169-194. The reference evaluates a Silero model through
+  // whisper.cpp's CPU VAD (whisper_vad_detect_speech); neither that code nor the model file is part of this
+  // build, so the gate is a hook: return false for "no speech" and the request gets the reference's
+  // placeholder result (:173-192) without touching the GPU. Without a hook the gate is open, which is what
+  // the reference does when its VAD context failed to load (vad_ctx_ == nullptr -> true, :109); the
+  // constructor says so loudly when Settings.enable_vad asks for a gate that is not there.
+  using VadFn = std::function<bool(const float* pcm, size_t n_samples)>;
+  void set_vad_fn(VadFn fn) { vad_fn_ = std::move(fn); }
+  bool vad_gate_active() const { return settings_.enable_vad && (bool)vad_fn_; }
   long batches_run() const { return batches_run_; }
   long requests_batched() const { return requests_batched_; }
 
@@ -98,6 +107,8 @@ class SttEngine {
   Settings settings_;
   sw_ctx* ctx_ = nullptr;
   ProsodyFn prosody_fn_;  // empty: the batched GPU path (sw_prosody_segments_*)
+  VadFn vad_fn_;          // empty: no speech pre-gate (see set_vad_fn)
+  std::mutex vad_mutex_;  // the reference serialises VAD calls (stt_engine.cpp:110)
 
   // admission: at most parallel_requests requests in the engine (the reference's whisper_state pool)
   std::mutex pool_mutex_;

@@ -53,6 +53,10 @@ inline DecodedAudio parse_wav_robust(const std::string& bytes) {
       memcpy(&out.channels, data + pos + 2, 2);
       memcpy(&out.sample_rate, data + pos + 4, 4);
       memcpy(&bits, data + pos + 14, 2);
+      // not in the reference: a header with 0 channels reaches `n_samples / channels` below (SIGFPE on an
+      // untrusted upload, utils.h:194), and a 0 Hz rate only fails much later; both are malformed files
+      if (out.channels < 1) throw std::runtime_error("Invalid channel count");
+      if (out.sample_rate <= 0) throw std::runtime_error("Invalid sample rate");
       have_fmt = true;
       pos += size;
     } else if (memcmp(id, "data", 4) == 0) {

@@ -95,6 +95,18 @@ def test_restatement_properties(ours):
         assert len(ours(c[ok])[0]) == 1000, ok
 
 
+def test_malformed_headers_the_reference_crashes_on_are_rejected(ours):
+    """A 0-channel header divides by zero in the reference (utils.h:194-199: SIGFPE, so it cannot be a parity
+    case); a 0 Hz / negative rate only fails downstream. The restatement rejects both like any other bad file."""
+    mono = np.arange(100, dtype=np.int16)
+    assert ours(wav(mono, channels=0)) is None
+    assert ours(wav(mono, rate=0)) is None
+    hdr = bytearray(wav(mono))
+    hdr[24:28] = struct.pack("<i", -8000)
+    assert ours(bytes(hdr)) is None
+    assert len(ours(wav(mono, channels=1, rate=8000))[0]) == 100
+
+
 def test_restatement_matches_the_reference_build(ours, ref):
     if ref is None:
         pytest.skip("oracle/_ref/libref_wav.so not built here (no /root/reference)")

@@ -28,6 +28,12 @@ CASES = [
     (1501, 392, 200, 0, True, True, 512),
     (1000, 640, 512, 7, True, True, 512),     # row bias + GELU + residual
     (4096, 2560, 1280, 0, True, False, 0),    # cross-KV shape: the engine's dispatch picks the pair kernel (M >= 2048)
+    # the benchmarked configuration's own shapes (large-v3: d = 1280, FC2 K = 5120, n_vocab = 51866)
+    (3000, 1280, 5120, 2, True, True, 512),   # FC2: K = 5120, f32 residual, CTA-pair kernel
+    (3000, 1280, 5120, 2, True, True, 0),     # ... as the engine dispatches it
+    (3000, 3840, 1280, 0, True, False, 512),  # QKV
+    (64, 51866, 1280, 2, False, False, 0),    # decoder logits of one greedy batch: N = n_vocab (ragged), f32 out
+    (320, 51866, 1280, 2, False, False, 0),   # ... of 64 windows x 5 beams
 ]
 
 
@@ -68,3 +74,55 @@ def test_gemm_is_bit_reproducible_and_pair_equals_single(gemm_check):
         outs.append(C)
     assert torch.equal(outs[0], outs[3]) and torch.equal(outs[1], outs[2])
     assert torch.equal(outs[0], outs[1])
+
+
+SKINNY = [
+    # R, N, K, split (0 = the engine's plan), bias, gelu        -- large-v3 decoder-step shapes
+    (64, 3840, 1280, 1, True, 0),     # QKV
+    (64, 1280, 1280, 0, False, 0),    # d x d projections: split-K partials
+    (64, 5120, 1280, 1, True, 1),     # FC1 + GELU
+    (64, 1280, 5120, 0, False, 0),    # FC2: K = 5120, split-K partials
+    (7, 1280, 5120, 0, False, 0),     # a ragged row block
+    (320, 3840, 1280, 1, True, 0),    # 64 windows x 5 beams: five row blocks
+    (33, 384, 384, 0, False, 0),      # tiny widths
+    (64, 1536, 384, 1, True, 1),
+]
+
+
+@pytest.mark.parametrize("case", SKINNY, ids=lambda c: "R%d_N%d_K%d_s%d" % c[:4])
+def test_skinny_gemm_matches_fp32_reference(gemm_check, case):
+    """The decoder step's weight-streaming GEMM (skinny_gemm.cu) against torch fp32 on the same bf16 inputs:
+    bf16 out within one bf16 rounding of the range, split-K f32 partials summed within 1e-3 of the range."""
+    import ctypes
+    import torch
+    R, N, K, split, bias, gelu = case
+    lib = gemm_check.lib
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    lib.sw_dev_skinny_gemm.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp, vp, ci, vp]
+    g = torch.Generator(device="cuda").manual_seed(R + N + K)
+    X = (torch.randn(R, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g) if bias else None
+    sp = split if split > 0 else lib.sw_dev_skinny_split(N, K)
+    ref = X.float() @ W.float().t()
+    if sp == 1:
+        out = torch.full((R, N), 7.0, device="cuda", dtype=torch.bfloat16)
+        rc = lib.sw_dev_skinny_gemm(X.data_ptr(), W.data_ptr(), R, N, K, b.data_ptr() if bias else None, gelu,
+                                    out.data_ptr(), None, 1, None)
+        assert rc == 0, lib.sw_last_error()
+        torch.cuda.synchronize()
+        if bias:
+            ref = ref + b[None]
+        if gelu:
+            ref = torch.nn.functional.gelu(ref, approximate="tanh")
+        tol = 1e-2
+        got = out.float()
+    else:
+        part = torch.full((sp, R, N), 7.0, device="cuda")
+        rc = lib.sw_dev_skinny_gemm(X.data_ptr(), W.data_ptr(), R, N, K, None, 0, None, part.data_ptr(), sp, None)
+        assert rc == 0, lib.sw_last_error()
+        torch.cuda.synchronize()
+        got = part.sum(0)
+        tol = 1e-3
+    scale = max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().max().item() <= tol * scale

@@ -57,11 +57,9 @@ def test_mel_parity_ragged_lengths(eng_micro, ora_micro, seconds):
     assert np.array_equal(got, got32)  # int16 entry == the reference's /32768 host loop + f32 entry
 
 
-def test_mel_parity_128_bins_and_extremes(swb, ora):
+def test_mel_parity_extremes(swb, ora):
+    """Full-scale, silent and white-noise inputs on the 80-bin front end."""
     path, _ = model_file("micro", seed=77, script_len=0)
-    # same micro model but with a 128-bin filterbank is not a valid hparam combo for conv1, so the
-    # 128-mel front end is exercised through a large-v3-shaped header on the smallest widths: tiny
-    # would be 80; instead check full-scale and silent inputs on the 80-bin model
     e = swb.Engine(path, max_batch=2)
     o = ora.Oracle(path)
     for pcm16 in (np.full(16000 * 3, 32767, np.int16), np.full(16000 * 3, -32768, np.int16),
@@ -71,6 +69,87 @@ def test_mel_parity_128_bins_and_extremes(swb, ora):
         got = e.mel_pcm16(pcm16)
         assert np.abs(got - want).max() <= 1e-3 * max(1.0, np.abs(want).max())
     e.close()
+
+
+# ---------------------------------------------------------------- the benchmarked widths (large-v3)
+# Stage parity at the dimensions bench.py runs: 128 mel bins, d = 1280, 20 heads, FC K = 5120,
+# n_vocab = 51866 ("large-v3-2l" = large-v3 with 2 + 2 layers, so that the oracle finishes in seconds).
+@pytest.fixture(scope="module")
+def lv3(swb, ora):
+    path, info = model_file("large-v3-2l", script_len=40)
+    e = swb.Engine(path, max_batch=4, max_beams=5)
+    assert (e.info.n_mels, e.info.n_audio_state, e.info.n_audio_head, e.info.n_vocab) == (128, 1280, 20, 51866)
+    o16 = ora.Oracle(path, weight_round=False, act_round=ora.ACT_F16)
+    yield e, o16, path, info
+    e.close()
+
+
+@pytest.mark.parametrize("seconds", [0.0, 0.7, 5.33, 30.0, 41.5])
+def test_mel_parity_128_bins(lv3, seconds):
+    e, o, _, _ = lv3
+    pcm16 = synth_audio.utterance(5, int(seconds * 10), seconds=max(seconds, 0.01))[: int(seconds * 16000)]
+    want, _ = o.mel(synth_audio.to_f32(pcm16))
+    got = e.mel_pcm16(pcm16)
+    assert got.shape == want.shape and got.shape[0] == 128
+    assert np.abs(got - want).max() <= 1e-3 * max(1.0, np.abs(want).max())   # north_star: 1e-3 relative
+    assert np.array_equal(got, e.mel_f32(synth_audio.to_f32(pcm16)))
+
+
+def test_mel_parity_128_bins_extremes(lv3):
+    e, o, _, _ = lv3
+    for pcm16 in (np.full(16000 * 2, 32767, np.int16), np.full(16000 * 2, -32768, np.int16),
+                  np.zeros(16000 * 2, np.int16),
+                  (np.random.default_rng(2).integers(-32768, 32767, 16000 * 2)).astype(np.int16)):
+        want, _ = o.mel(synth_audio.to_f32(pcm16))
+        got = e.mel_pcm16(pcm16)
+        assert np.abs(got - want).max() <= 1e-3 * max(1.0, np.abs(want).max())
+
+
+def test_encoder_parity_large_v3_widths(lv3, ora):
+    """conv stem (K = 3*128 / 3*1280), CTA-pair GEMMs at K = 1280 and K = 5120, 20-head tcgen05 attention,
+    ln_post: encoder output vs the oracle in whisper.cpp-mode numerics (f16) and at the engine's own
+    rounding points (bf16)."""
+    e, o16, path, _ = lv3
+    pcm = synth_audio.to_f32(synth_audio.utterance(5, 1))
+    mel, _ = o16.mel(pcm)
+    wins = np.stack([mel[:, :3000], mel[:, 700:3700]])
+    got = e.encode(wins)
+    ob = ora.Oracle(path, weight_round=True, act_round=ora.ACT_BF16)
+    for i in range(2):
+        want16 = o16.encode(wins[i])
+        assert rel(got[i], want16) < 2e-2
+        assert np.sqrt(((got[i] - want16) ** 2).mean()) / want16.std() < 5e-3
+        assert rel(got[i], ob.encode(wins[i])) < 1e-2
+
+
+def test_decoder_logits_parity_large_v3_widths(lv3):
+    """Teacher-forced decoder at d = 1280 / 20 heads / n_vocab = 51866 over the cross-KV of two different
+    windows: skinny GEMMs at the bench's shapes, paged self attention, tensor-core cross attention, logits
+    GEMM with N = 51866."""
+    e, o16, _, info = lv3
+    sp = info["special"]
+    pcm = synth_audio.to_f32(synth_audio.utterance(5, 2))
+    mel, _ = o16.mel(pcm)
+    wins = np.stack([mel[:, :3000], mel[:, 500:3500]])
+    e.encode(wins, want_output=False)
+    toks = np.array([sp["sot"], sp["sot"] + 1, sp["transcribe"]] + info["script"][:21], np.int32)
+    got = e.decode_logits(np.stack([toks, toks]))
+    assert got.shape == (2, len(toks), 51866)
+    for w in range(2):
+        o16.encode(wins[w])
+        want = o16.decode(toks, 0)
+        assert rel(got[w], want) < 1e-2
+        assert (got[w].argmax(1) == want.argmax(1)).all()
+    assert not np.array_equal(got[0], got[1])  # the two windows' audio reaches the logits
+
+
+def test_greedy_identical_large_v3_widths(lv3):
+    e, o16, _, _ = lv3
+    clips = [synth_audio.utterance(5, 3), synth_audio.utterance(5, 4, seconds=11.0)]
+    got = e.full_batch_pcm16(clips, e.default_params(0, **GREEDY))
+    po = o16.default_params(0, **GREEDY)
+    for c, g in zip(clips, got):
+        compare_results(g, o16.full(synth_audio.to_f32(c), po))
 
 
 # ---------------------------------------------------------------- encoder / decoder stages

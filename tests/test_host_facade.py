@@ -112,20 +112,32 @@ def test_concurrent_streams_share_device_passes(tmp_path):
 
 @pytest.mark.gpu
 def test_facade_resamples_non_16k_input(tmp_path):
-    """stt_engine.cpp:138-145: input that is not 16 kHz is converted first (here by sw_resample_f32): a 48 kHz
-    copy of a clip transcribes to the same tokens as the clip."""
-    from scipy.signal import resample_poly
+    """stt_engine.cpp:138-145: input that is not 16 kHz is converted first (here by sw_resample_f32). Run on the
+    keyed model, whose transcript is decided by the audio: the symbols of a clip rendered at 48 kHz (and at
+    22.05 kHz) come back exactly; the same 48 kHz samples declared as 16 kHz (= no conversion: a third of the
+    pitch) do NOT - a broken or skipped resampler fails this test."""
+    from tools import gen_model, ggml_io
     build_host()
-    path, info = model_file("tiny")
-    clip = synth_audio.utterance(3, 23, seconds=9.0)
-    clip48 = np.clip(np.round(resample_poly(clip.astype(np.float64), 3, 1)), -32768, 32767).astype(np.int16)
-    outs = []
-    for name, data, rate in (("a.raw", clip, 16000), ("b.raw", clip48, 48000)):
+    path, info = model_file("tiny", script_len=40, keyed=4)
+    k = info["keyed"]
+    _, _, vocab, _ = ggml_io.read_ggml(path)
+    sy = synth_audio.keyed_symbols(k, 31)
+    eot = info["special"]["eot"]
+    want = [vocab[t].decode("utf-8", "replace") for t in gen_model.keyed_expected_tokens(info, sy) if t < eot]
+    assert len(want) == len(k["slots"])
+
+    def run(name, data, rate):
         raw = tmp_path / name
         data.tofile(raw)
         r = subprocess.run([os.path.join(HOST, "build", "stt_cli"), os.path.dirname(path), os.path.basename(path),
                             str(raw), "1", "1", "batch", str(rate)], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
-        outs.append(json.loads(r.stdout.strip().splitlines()[0]))
-    toks = [[t[0] for s in o["segments"] for t in s["tokens"]] for o in outs]
-    assert toks[0] and toks[0] == toks[1]
+        o = json.loads(r.stdout.strip().splitlines()[0])
+        return [t[0] for s in o["segments"] for t in s["tokens"]]
+
+    to16 = lambda x: np.round(np.clip(x, -1, 1) * 32767.0).astype(np.int16)
+    assert run("a.raw", synth_audio.keyed_clip(k, sy, seed=31), 16000) == want
+    c48 = to16(synth_audio.keyed_clip(k, sy, seed=31, sr=48000))
+    assert run("b.raw", c48, 48000) == want
+    assert run("c.raw", to16(synth_audio.keyed_clip(k, sy, seed=31, sr=22050)), 22050) == want
+    assert run("d.raw", c48, 16000) != want

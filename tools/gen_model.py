@@ -318,7 +318,9 @@ def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, l
         js = cand[np.round(np.linspace(0, len(cand) - 1, J)).astype(int)]
         enc_pos_ch = np.concatenate([js, half + js])            # sin | cos columns of the sinusoid table
         enc_band_ch = np.array([half - 1 - k for k in range(K)])  # slowest sin columns (overwritten with 0)
+        enc_zero_ch = half - 1 - K                              # stays 0: LayerNorm's (0 - mean) / std = the offset
         dec_q_ch = np.arange(d - 2 * J, d)                      # decoder channels that carry sin | cos of tau(p)
+        dec_zero_ch = d - 2 * J - 1                             # to subtract from every other reserved channel
         centers = mel_centers_hz(n_mel)
         band_bins = [np.flatnonzero(np.abs(centers / f - 1.0) <= KEYED_BAND_REL) for f in KEYED_TONES_HZ[:K]]
         assert all(len(b) > 0 for b in band_bins)
@@ -326,7 +328,9 @@ def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, l
         # and of the noise floor, so that every band channel reads ~0 when idle and ~1.5 when active
         band_levels = [probe_band_levels(fb, band_bins[k], KEYED_TONES_HZ[k], 0.34, 0.003) for k in range(K)]
         kp = dict(J=J, omega=omega[js], enc_pos_ch=enc_pos_ch, enc_band_ch=enc_band_ch, dec_q_ch=dec_q_ch,
-                  enc_reserved=np.concatenate([enc_pos_ch, enc_band_ch]))
+                  enc_zero_ch=enc_zero_ch, dec_zero_ch=dec_zero_ch,
+                  enc_reserved=np.concatenate([enc_pos_ch, enc_band_ch, [enc_zero_ch]]),
+                  dec_reserved=np.concatenate([dec_q_ch, [dec_zero_ch]]))
 
     def normal(shape, std):
         return rng.standard_normal(size=shape, dtype=np.float32) * np.float32(std)
@@ -368,6 +372,7 @@ def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, l
     c2w, c2b = normal((d, d, 3), 1.0 / np.sqrt(3 * d)), normal((d, 1), 0.01)
     if K:
         enc_pos[:, kp["enc_band_ch"]] = 0.0
+        enc_pos[:, kp["enc_zero_ch"]] = 0.0
         for k in range(K):  # band channel k = mean log-mel of band k over 3 frames, passed through conv2 as is
             ch = kp["enc_band_ch"][k]
             c1w[ch] = 0.0
@@ -378,8 +383,9 @@ def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, l
             c2w[ch] = 0.0
             c2w[ch, ch, :] = 1.0 / 3.0
             c2b[ch] = 0.0
-        c2w[kp["enc_pos_ch"]] = 0.0  # position channels: GELU(0) = 0, + the sinusoids
-        c2b[kp["enc_pos_ch"]] = 0.0
+        for chs in (kp["enc_pos_ch"], [kp["enc_zero_ch"]]):  # position channels: GELU(0) = 0, + the sinusoids
+            c2w[chs] = 0.0
+            c2b[chs] = 0.0
     wr.tensor("encoder.positional_embedding", enc_pos, False)
     wr.tensor("encoder.conv1.weight", c1w, f16)
     wr.tensor("encoder.conv1.bias", c1b, False)
@@ -408,13 +414,14 @@ def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, l
         if K:
             script, variants, slots, text_index = make_keyed_script(sp, script_len, seed + 2, n_base - 1, K)
             J, qch = kp["J"], kp["dec_q_ch"]
+            rch = kp["dec_reserved"]
             wrng = np.random.default_rng(seed + 3)
             wdir = wrng.standard_normal((K, d))
-            wdir[:, qch] = 0.0
+            wdir[:, rch] = 0.0
             wdir = np.linalg.qr(wdir.T)[0].T.astype(np.float32)   # K orthonormal directions, zero on the q channels
             kp["wdir"] = wdir
-            tok_emb[:, qch] = 0.0
-            pos_emb[:, qch] = 0.0
+            tok_emb[:, rch] = 0.0
+            pos_emb[:, rch] = 0.0
             delta = keyed_delta * emb_std * np.sqrt(d)            # |delta w_k| = keyed_delta * |e|
             e16 = tok_emb.astype(np.float16).astype(np.float32)
             ti = 0
@@ -435,8 +442,8 @@ def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, l
             keyed_info = dict(K=K, variants=variants, slots=slots, text_index=text_index,
                               tones_hz=[keyed_tone_hz(k) for k in range(K)])
             # keyed_beta is relative: the band term written into the stream has about keyed_beta times the
-            # norm of the scripted term (band values after ln_post: ~ +0.4 active, ~ -0.45 idle)
-            kp["beta"] = keyed_beta * script_rms * np.sqrt(d) / 0.9
+            # norm of the scripted term (band values after ln_post, offset removed: ~2 active, 0 idle)
+            kp["beta"] = keyed_beta * script_rms * np.sqrt(d) / 2.0
             extra_var = (J * 1.0) / d + (keyed_beta * script_rms) ** 2
         else:
             script = make_script(sp, script_len, seed + 2, n_base - 1, end_cs=script_end_cs,
@@ -464,7 +471,7 @@ def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, l
     wr.tensor("decoder.positional_embedding", pos_emb, False)
     wr.tensor("decoder.token_embedding.weight", tok_emb, f16)
     del tok_emb
-    dec_keep = kp["dec_q_ch"] if K else None
+    dec_keep = kp["dec_reserved"] if K else None
 
     def alignment_head(t):
         # head 0 (rows / columns 0..63) of the last layer's cross attention
@@ -473,11 +480,16 @@ def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, l
             t[name][:64] = 0.0
         t["qb"][:64] = 0.0
         t["vb"][:64] = 0.0
+        # every read subtracts the always-zero channel: LayerNorm maps a channel x to (x - mean) / std, so the
+        # difference is x / std - the data-dependent offset is gone (q is exactly 0 where pos_emb holds no time)
         for r in range(2 * J):
             t["qw"][r, kp["dec_q_ch"][r]] = a
+            t["qw"][r, kp["dec_zero_ch"]] = -a
             t["kw"][r, kp["enc_pos_ch"][r]] = a
+            t["kw"][r, kp["enc_zero_ch"]] = -a
         for k in range(K):
             t["vw"][k, kp["enc_band_ch"][k]] = 1.0
+            t["vw"][k, kp["enc_zero_ch"]] = -1.0
         t["ow"][:, :64] = 0.0
         for k in range(K):
             t["ow"][:, k] = kp["beta"] * kp["wdir"][k]

@@ -335,6 +335,102 @@ def test_temperature_fallback_path_runs(swb, ora):
     e.close()
 
 
+@pytest.fixture(scope="module")
+def keyed_tiny(swb, ora):
+    path, info = model_file("tiny", script_len=40, keyed=4)
+    e = swb.Engine(path, max_batch=8, max_beams=5)
+    k = info["keyed"]
+    seeds = list(range(60, 68))
+    clips = [synth_audio.keyed_clip(k, synth_audio.keyed_symbols(k, s), seed=s) for s in seeds]
+    yield e, path, info, clips
+    e.close()
+
+
+LADDER = [
+    # a threshold the T = 0 pass fails (mean log p ~ -0.1): the ladder runs, and the sharpened pass succeeds
+    dict(logprob_thold=-0.05, temperature_inc=0.2, best_of=2),
+    dict(logprob_thold=-0.05, temperature_inc=0.4, best_of=5),
+    dict(temperature=0.2, temperature_inc=0.2, best_of=2),   # start on the ladder
+    dict(temperature=0.4, temperature_inc=0.2, best_of=5),
+    dict(temperature=0.8, temperature_inc=0.2, best_of=5),
+]
+
+
+@pytest.mark.parametrize("kw", LADDER, ids=lambda k: "_".join("%s%s" % (a[:4], b) for a, b in k.items()))
+def test_fallback_ladder_token_by_token(keyed_tiny, ora, kw):
+    """Temperature fallback and best_of sampling, token by token: the T > 0 passes draw from softmax(logits / T)
+    with uniforms both sides generate identically (mt19937 -> generate_canonical), best_of decoders are ranked
+    by whisper_sequence_score, the winner's tokens, times and probabilities are compared with the oracle.
+    On the keyed model the sharpened distributions put >= 0.99 on one token, so no draw sits near a CDF
+    boundary and the comparison is exact."""
+    e, path, info, clips = keyed_tiny
+    o = ora.Oracle(path, weight_round=False, act_round=ora.ACT_F16)
+    full = dict(language="en", suppress_nst=1, token_timestamps=1, **kw)
+    got = e.full_batch_pcm16(clips[:4], e.default_params(0, **full))
+    greedy = e.full_batch_pcm16(clips[:1], e.default_params(0, **GREEDY))[0]
+    for c, g in zip(clips[:4], got):
+        want = o.full(synth_audio.to_f32(c), o.default_params(0, **full))
+        compare_results(g, want)
+        assert g["n_decode_steps"] == want["n_decode_steps"]
+    if "logprob_thold" in kw:  # the ladder really ran: more decoder steps than the greedy pass alone, sharper p
+        assert got[0]["n_decode_steps"] > greedy["n_decode_steps"]
+        assert min(t["p"] for s in got[0]["segments"] for t in s["tokens"]) > \
+               min(t["p"] for s in greedy["segments"] for t in s["tokens"])
+
+
+def test_sampling_at_temperature_one_margin_aware(keyed_tiny, ora):
+    """T = 1: real sampling (a tenth of the draws leave the top token), so a draw can land within the bf16
+    probability error of a CDF boundary. Same rounding points (bf16-mode oracle): >= 3 of 4 clips identical,
+    >= 90 % of the tokens everywhere."""
+    e, path, info, clips = keyed_tiny
+    ob = ora.Oracle(path, weight_round=True, act_round=ora.ACT_BF16)
+    full = dict(language="en", suppress_nst=1, temperature=1.0, temperature_inc=0.0, best_of=5, logprob_thold=-5.0)
+    got = e.full_batch_pcm16(clips[:4], e.default_params(0, **full))
+    same = 0
+    for c, g in zip(clips[:4], got):
+        a, b = seg_ids(g), seg_ids(ob.full(synth_audio.to_f32(c), ob.default_params(0, **full)))
+        n = min(len(a), len(b))
+        assert sum(x == y for x, y in zip(a, b)) >= 0.9 * max(len(a), len(b)) or n == 0
+        same += a == b
+    assert same >= 3
+
+
+def test_beam_search_identical_on_keyed_model(keyed_tiny, ora):
+    """Beam search (5 beams, the service default) on 8 different clips against the whisper.cpp-mode oracle:
+    identical tokens, times and probabilities on every clip (north_star: >= 99 % of segments)."""
+    from tools import gen_model
+    e, path, info, clips = keyed_tiny
+    o = ora.Oracle(path, weight_round=False, act_round=ora.ACT_F16)
+    kw = dict(language="en", temperature_inc=0.0, suppress_nst=1, token_timestamps=1, beam_size=5)
+    got = e.full_batch_pcm16(clips, e.default_params(1, **kw))
+    k = info["keyed"]
+    for s, c, g in zip(range(60, 68), clips, got):
+        compare_results(g, o.full(synth_audio.to_f32(c), o.default_params(1, **kw)))
+        assert seg_ids(g) == gen_model.keyed_expected_tokens(info, synth_audio.keyed_symbols(k, s))
+
+
+def test_by_value_logit_config_is_not_baked_into_the_step_graph(swb, ora):
+    """the decode step is replayed from a CUDA graph, and process_logits takes suppress_blank and the
+    max_initial_ts bound BY VALUE - a later call with other values on the same context must not replay the old
+    ones. The model's script opens at <|2.00|>: with max_initial_ts = 1.0 (default) that token is masked and
+    another one is chosen, with max_initial_ts = 0 (rule off) the script is followed. Each call is checked
+    against the oracle under the same parameters, in both orders, with step graphs on."""
+    path, info = model_file("micro", script_len=30, script_first_ts=100)
+    e = swb.Engine(path, max_batch=2)
+    o = ora.Oracle(path)
+    clip = synth_audio.utterance(3, 30, seconds=10.0)
+    outs = {}
+    for mi, sb in ((1.0, 1), (0.0, 1), (1.0, 1), (0.0, 0), (1.0, 0)):
+        kw = dict(GREEDY, max_initial_ts=mi, suppress_blank=sb)
+        got = e.full_batch_pcm16([clip], e.default_params(0, **kw))[0]
+        compare_results(got, o.full(synth_audio.to_f32(clip), o.default_params(0, **kw)))
+        key = (seg_ids(got), got["segments"][0]["t0"])
+        outs.setdefault((mi, sb), key)
+        assert outs[(mi, sb)] == key
+    assert outs[(0.0, 1)][1] == 200 and outs[(1.0, 1)][1] != 200   # <|2.00|> opens the transcript only with the rule off
+    e.close()
+
+
 def test_abort_callback_and_errors(swb, micro_model, eng_micro):
     calls = []
 

@@ -141,3 +141,56 @@ def test_facade_resamples_non_16k_input(tmp_path):
     assert run("b.raw", c48, 48000) == want
     assert run("c.raw", to16(synth_audio.keyed_clip(k, sy, seed=31, sr=22050)), 22050) == want
     assert run("d.raw", c48, 16000) != want
+
+
+@pytest.mark.gpu
+def test_facade_serves_request_overrides_above_the_settings(tmp_path):
+    """RequestOptions.beam_size / best_of override the Settings per request (stt_engine.cpp:204-209)
+    and whisper.cpp serves up to 8 decoders: a request with beam 8 (settings: 1) and one with best_of 7 must be
+    served, not dropped, and must not fail the other requests of their device pass."""
+    from tools import gen_model, ggml_io
+    build_host()
+    path, info = model_file("tiny", script_len=40, keyed=4)
+    k = info["keyed"]
+    _, _, vocab, _ = ggml_io.read_ggml(path)
+    sy = synth_audio.keyed_symbols(k, 33)
+    want = [vocab[t].decode("utf-8", "replace") for t in gen_model.keyed_expected_tokens(info, sy)
+            if t < info["special"]["eot"]]
+    raw = tmp_path / "clip.raw"
+    synth_audio.keyed_clip(k, sy, seed=33).tofile(raw)
+    cli = os.path.join(HOST, "build", "stt_cli")
+    for extra in (["req_beam=8"], ["req_beam=1", "req_best_of=7", "req_temperature=0.2"]):
+        r = subprocess.run([cli, os.path.dirname(path), os.path.basename(path), str(raw), "3", "1", "batch", "16000"] + extra,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs = [json.loads(l) for l in r.stdout.strip().splitlines()]
+        assert len(outs) == 3
+        for o in outs:
+            assert [t[0] for s in o["segments"] for t in s["tokens"]] == want, extra
+
+
+@pytest.mark.gpu
+def test_facade_vad_gate_returns_the_reference_placeholder(tmp_path):
+    """stt_engine.cpp:169-194: with enable_vad and a gate that says "no speech", the request gets ONE placeholder
+    result (text "", language "unknown", speaker "unknown", t1 = samples / 16) and Whisper is not run; with
+    speech the gate lets the request through. The Silero model is not in this build: the gate is the facade's
+    hook (stt_cli vad=energy installs an energy detector)."""
+    build_host()
+    path, info = model_file("tiny", script_len=40, keyed=4)
+    k = info["keyed"]
+    cli = os.path.join(HOST, "build", "stt_cli")
+    silent = tmp_path / "silent.raw"
+    np.zeros(16000 * 4, np.int16).tofile(silent)
+    r = subprocess.run([cli, os.path.dirname(path), os.path.basename(path), str(silent), "1", "1", "batch", "16000",
+                        "enable_vad=1", "vad=energy"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    o = json.loads(r.stdout.strip().splitlines()[0])
+    assert o["batches_run"] == 0 and len(o["segments"]) == 1
+    s = o["segments"][0]
+    assert (s["text"], s["language"], s["speaker"], s["t0"], s["t1"], s["tokens"]) == ("", "unknown", "unknown", 0, 4000, [])
+    speech = tmp_path / "speech.raw"
+    synth_audio.keyed_clip(k, synth_audio.keyed_symbols(k, 34), seed=34).tofile(speech)
+    r = subprocess.run([cli, os.path.dirname(path), os.path.basename(path), str(speech), "1", "1", "batch", "16000",
+                        "enable_vad=1", "vad=energy"], capture_output=True, text=True, timeout=300)
+    o = json.loads(r.stdout.strip().splitlines()[0])
+    assert o["batches_run"] == 1 and len(o["segments"]) >= 2 and o["segments"][0]["language"] == "en"

@@ -154,7 +154,7 @@ def make_vocab(n_base, seed):
     return toks[:n_base]
 
 
-def make_script(sp, n_tokens, seed, n_vocab_text, end_cs=3000, final_pair=False):
+def make_script(sp, n_tokens, seed, n_vocab_text, end_cs=3000, final_pair=False, first_ts=0):
     """A valid timestamp-token transcript of n_tokens sampled tokens ending in EOT.
     end_cs: last timestamp in centiseconds/2 units (1500 = 30.00 s)."""
     rng = np.random.default_rng(seed)
@@ -163,7 +163,8 @@ def make_script(sp, n_tokens, seed, n_vocab_text, end_cs=3000, final_pair=False)
     n_seg = max(1, n_tokens // 14)
     last = min(end_cs // 2, 1500)
     cuts = np.sort(rng.choice(np.arange(20, last - 20), size=n_seg - 1, replace=False)) if n_seg > 1 else []
-    bounds = [0] + [int(c) for c in cuts] + [last]
+    bounds = [int(first_ts)] + [int(c) for c in cuts if int(c) > first_ts] + [last]
+    n_seg = len(bounds) - 1
     bounds[-1] = min(bounds[-1], 1500)
     # budget: per segment 2 timestamps + text; final EOT
     n_text_total = n_tokens - 1 - 2 * n_seg
@@ -276,7 +277,7 @@ class GgmlWriter:
 
 def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, ln_f_gain=None,
              script_end_cs=3000, w_std=0.02, emb_std=0.02, f32_all=False, verbose=False,
-             script_final_pair=False, keyed=0, keyed_beta=0.6, keyed_delta=1.2, keyed_attn=2.5,
+             script_final_pair=False, script_first_ts=0, keyed=0, keyed_beta=0.6, keyed_delta=1.2, keyed_attn=2.5,
              keyed_gain=0.7):
     d, n_head, n_layer, n_mel, n_vocab = SIZES[size]
     if seed is None:
@@ -447,7 +448,7 @@ def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, l
             extra_var = (J * 1.0) / d + (keyed_beta * script_rms) ** 2
         else:
             script = make_script(sp, script_len, seed + 2, n_base - 1, end_cs=script_end_cs,
-                                 final_pair=script_final_pair)
+                                 final_pair=script_final_pair, first_ts=script_first_ts)
             e16 = tok_emb.astype(np.float16).astype(np.float32)
             for i, tok in enumerate(script):
                 p = p0 - 1 + i  # input position whose output predicts script[i]

@@ -200,11 +200,12 @@ def test_decoder_logits_parity(eng_tiny, ora_tiny, tiny_model):
 
 
 # ---------------------------------------------------------------- whole path
-def compare_results(got, want, p_tol=1e-2):
+def compare_results(got, want, p_tol=1e-2, check_windows=True):
     assert seg_ids(got) == seg_ids(want)
     assert [(s["t0"], s["t1"], s["text"]) for s in got["segments"]] == \
            [(s["t0"], s["t1"], s["text"]) for s in want["segments"]]
-    assert got["n_windows"] == want["n_windows"]
+    if check_windows:
+        assert got["n_windows"] == want["n_windows"]
     for sg, sw_ in zip(got["segments"], want["segments"]):
         for a, b in zip(sg["tokens"], sw_["tokens"]):
             assert abs(a["p"] - b["p"]) < p_tol
@@ -370,7 +371,10 @@ def test_fallback_ladder_token_by_token(keyed_tiny, ora, kw):
     greedy = e.full_batch_pcm16(clips[:1], e.default_params(0, **GREEDY))[0]
     for c, g in zip(clips[:4], got):
         want = o.full(synth_audio.to_f32(c), o.default_params(0, **full))
-        compare_results(g, want)
+        # p at temperature T is softmax(logits / T): a logit difference between bf16 and f16 numerics is divided
+        # by T as well (x 5 at T = 0.2), so the 1e-2 bound of the T = 0 comparisons becomes 3e-2 here; the
+        # engine's n_windows counts decode passes (a re-run counts again), the oracle's counts encoded windows
+        compare_results(g, want, p_tol=3e-2, check_windows=False)
         assert g["n_decode_steps"] == want["n_decode_steps"]
     if "logprob_thold" in kw:  # the ladder really ran: more decoder steps than the greedy pass alone, sharper p
         assert got[0]["n_decode_steps"] > greedy["n_decode_steps"]

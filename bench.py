@@ -135,7 +135,8 @@ def run_reference(args, rank, world):
     path = ensure_model(args.model, args.script_len)
     cores = os.cpu_count() or 1
     o = ora.Oracle(path, weight_round=False, act_round=ora.ACT_F16, threads=cores)
-    p = o.default_params(0, **SERVICE_PARAMS)
+    beam = int(CONFIGS[args.config].get("beam", 1))
+    p = o.default_params(1, beam_size=beam, **SERVICE_PARAMS) if beam > 1 else o.default_params(0, **SERVICE_PARAMS)
     times = []
     info = model_info(path)
     for s in range(args.warmup + args.steps):
@@ -152,8 +153,9 @@ def run_reference(args, rank, world):
         n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * total / len(times),
         higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16 weights, f32 accumulate",
         data="synthetic",
-        config=dict(workload="whisper %s greedy, one 30 s window per step (bounded sample of the "
-                             "128-window step)" % args.model, script_tokens=args.script_len),
+        config=dict(workload="whisper %s %s, one 30 s window per step (bounded sample of: %s)" %
+                             (args.model, "beam 5" if beam > 1 else "greedy", CONFIGS[args.config]["what"]),
+                    baseline_config=args.config, script_tokens=args.script_len),
         cpu_baseline=dict(value=val, unit="audio-sec/sec", cores=cores, kind="port",
                           sample="1 x 30 s window per step, %d steps; CPU restatement of whisper.cpp "
                                  "v1.8.2, not ggml" % args.steps),
@@ -162,19 +164,52 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+CONFIGS = {
+    # BASELINE.json configs[i-1]; 5 is the one the metric is quoted on (default)
+    1: dict(model="tiny", script_len=60, windows=1, batch=1, beam=1,
+            what="Whisper tiny greedy, ONE 30 s clip (the reference's own CPU-runnable case): the CPU arm beside it is "
+                 "the headline of this line"),
+    2: dict(model="base", script_len=60, windows=32, batch=32, beam=1,
+            what="Whisper base, batch of 32 x 30 s windows, mel + encoder + greedy decode"),
+    3: dict(model="small", script_len=60, windows=32, batch=32, beam=5,
+            what="Whisper small (12 + 12 layers), beam search with 5 beams over the paged self-KV cache, 32 x 30 s windows"),
+    4: dict(model="medium", script_len=60, total=256, batch=64, beam=1, ragged=True, langs=["en", "tr", "de", "ja"],
+            what="Whisper medium multilingual, 256 utterances of mixed 5-30 s length (language cycled over en/tr/de/ja) "
+                 "dealt to the ranks by descending length (dispatch.shard_utterances)"),
+    5: dict(model="large-v3", script_len=100, windows=128, batch=64, beam=1,
+            what="whisper large-v3 greedy batch-64, 128 x 30 s windows per GPU per step (BASELINE configs[4] share of one GPU)"),
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="large-v3")
-    ap.add_argument("--windows-per-gpu", type=int, default=128)
-    ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--script-len", type=int, default=100)
+    ap.add_argument("--config", type=int, default=5, choices=sorted(CONFIGS),
+                    help="BASELINE.json configs[N-1]; 5 (default) is the configuration the metric is quoted on")
+    ap.add_argument("--model", default=None)
+    ap.add_argument("--windows-per-gpu", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--script-len", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--oracle-windows", type=int, default=3, help="windows the CPU oracle also transcribes (parity + cpu_baseline)")
+    ap.add_argument("--facade", action="store_true",
+                    help="also measure the reference-facing class: caller threads on SttEngine::transcribe_pcm16 with "
+                         "pageable vectors (host/stt_cli bench mode) -> e2e_facade")
     args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.model:
+        cfg["model"] = args.model
+    if args.batch:
+        cfg["batch"] = args.batch
+    if args.script_len:
+        cfg["script_len"] = args.script_len
+    if args.windows_per_gpu:
+        cfg["windows"] = args.windows_per_gpu
+        cfg.pop("total", None)
+    args.model, args.batch, args.script_len = cfg["model"], cfg["batch"], cfg["script_len"]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -203,61 +238,95 @@ def main():
         ensure_model(args.model, args.script_len)
     barrier()
     path = model_path(args.model, args.script_len)
+    minfo = model_info(path)
 
     swb = load_binding()
-    from tools import synth_audio
+    from tools import gen_model, synth_audio
+    disp = importlib.util.spec_from_file_location("dispatch", os.path.join(PKG, "dispatch.py"))
+    dispatch = importlib.util.module_from_spec(disp)
+    disp.loader.exec_module(dispatch)
+    beam = int(cfg.get("beam", 1))
     eng = swb.Engine(path, device=local_rank, max_batch=args.batch, max_beams=5)
-    params = eng.default_params(0, **SERVICE_PARAMS)  # greedy, best_of 5, temperature_inc 0.2 (defaults)
     # host sequencer workers (the Settings.n_threads knob): this rank's share of the box's cores
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     cores_here = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
-    params.n_threads = max(2, min(16, cores_here // max(1, local_world)))
+    n_threads = max(2, min(16, cores_here // max(1, local_world)))
+    langs = cfg.get("langs", ["en"])
+
+    def make_params(lang):
+        kw = dict(SERVICE_PARAMS, language=lang)
+        p = eng.default_params(1, beam_size=beam, **kw) if beam > 1 else eng.default_params(0, **kw)
+        p.n_threads = n_threads  # greedy: best_of 5, temperature_inc 0.2 (defaults)
+        return p
+    params_by_lang = {lg: make_params(lg) for lg in langs}
     eng.set_kernel_timing(True)
 
-    # ---- inputs: W windows of 30 s int16, pinned host copy + device copy
-    W = args.windows_per_gpu
-    n_s = 480000
+    # ---- this rank's utterances: int16 PCM, pinned host copy + device copy
+    if cfg.get("ragged"):
+        total = int(cfg["total"])
+        durs = synth_audio.durations_config4(total)
+        mine = dispatch.shard_utterances(total, world, rank, lengths=durs)   # dealt by descending length
+        scaling = "strong"
+    else:
+        W0 = int(cfg["windows"])
+        durs = [30.0] * (W0 * world)
+        mine = dispatch.shard_utterances(W0 * world, world, rank)            # contiguous blocks: weak scaling
+        scaling = "weak"
+    W = len(mine)
+    n_samp = [int(round(durs[i] * 100)) * 160 for i in mine]
+    offs = np.concatenate([[0], np.cumsum(n_samp)]).astype(np.int64)
     L = swb.lib()
-    host = L.sw_host_alloc(W * n_s * 2)
+    host = L.sw_host_alloc(int(offs[-1]) * 2)
     if not host:
         raise SystemExit("pinned allocation failed: " + swb.last_error())
-    host_np = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_int16)), shape=(W, n_s))
-    minfo = model_info(path)
-    want_ids = []
-    for i in range(W):
-        host_np[i], ids = window_clip(minfo, rank * W + i)
+    host_np = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_int16)), shape=(int(offs[-1]),))
+    want_ids, n_sure = [], []
+    for j, i in enumerate(mine):
+        clip, ids = window_clip(minfo, i)
+        host_np[offs[j]:offs[j + 1]] = clip[: n_samp[j]]
         want_ids.append(ids)
+        # tokens a clip shorter than 30 s still decides (tone slots wholly inside the audio)
+        n_sure.append(len(ids) if n_samp[j] >= 480000 else gen_model.keyed_sure_prefix(minfo, n_samp[j]))
     dev = torch.from_numpy(host_np.copy()).cuda()
-    lens = (C.c_int * W)(*([n_s] * W))
     ptr16 = C.POINTER(C.c_int16)
-    host_ptrs = (ptr16 * W)(*[C.cast(host + i * n_s * 2, ptr16) for i in range(W)])
-    dev_ptrs = (ptr16 * W)(*[C.cast(dev.data_ptr() + i * n_s * 2, ptr16) for i in range(W)])
+    groups = []   # one C-ABI call per language (a call carries one sw_full_params)
+    for li, lg in enumerate(langs):
+        idx = [j for j in range(W) if mine[j] % len(langs) == li]
+        if not idx:
+            continue
+        n = len(idx)
+        groups.append(dict(
+            lang=lg, idx=idx, n=n, lens=(C.c_int * n)(*[n_samp[j] for j in idx]),
+            host=(ptr16 * n)(*[C.cast(host + int(offs[j]) * 2, ptr16) for j in idx]),
+            dev=(ptr16 * n)(*[C.cast(dev.data_ptr() + int(offs[j]) * 2, ptr16) for j in idx])))
 
     L.sw_result_token_data.restype = swb.TokenData
     parity = dict(windows=0, token_identical_to_expected=0, distinct_transcripts=0)
     seen, got_ids = set(), {}
 
-    def step(ptrs, check=False):
-        res = eng.full_batch_ptrs(ptrs, lens, W, params)
+    def step(which, check=False):
         n_tok = 0
-        for w, r in enumerate(res):
-            ids = []
-            for s in range(L.sw_result_n_segments(r)):
-                nt = L.sw_result_n_tokens(r, s)
-                n_tok += nt
+        for g in groups:
+            res = eng.full_batch_ptrs(g[which], g["lens"], g["n"], params_by_lang[g["lang"]])
+            for w, r in zip(g["idx"], res):
+                ids = []
+                for s in range(L.sw_result_n_segments(r)):
+                    nt = L.sw_result_n_tokens(r, s)
+                    n_tok += nt
+                    if check:
+                        ids += [L.sw_result_token_data(r, s, j).id for j in range(nt)]
                 if check:
-                    ids += [L.sw_result_token_data(r, s, j).id for j in range(nt)]
-            if check:
-                parity["windows"] += 1
-                parity["token_identical_to_expected"] += int(ids == want_ids[w])
-                seen.add(tuple(ids))
-                got_ids[w] = ids
-            L.sw_result_free(r)
+                    parity["windows"] += 1
+                    k = n_sure[w]
+                    parity["token_identical_to_expected"] += int(ids[:k] == want_ids[w][:k] and (k < len(want_ids[w]) or ids == want_ids[w]))
+                    seen.add(tuple(ids))
+                    got_ids[w] = ids
+                L.sw_result_free(r)
         return n_tok
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def timed(ptrs, k):
+    def timed(which, k):
         """K steps between a barrier + device synchronize on both sides, timed with two CUDA events. The device
         is idle when the first is recorded (synchronize just before) and every step call returns only after
         its last kernel and read-back have completed (the sequencer reads the picks of every decoder step), so
@@ -268,7 +337,7 @@ def main():
         ev0.record()
         n_tok = 0
         for _ in range(k):
-            n_tok += step(ptrs)
+            n_tok += step(which)
         ev1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -280,18 +349,24 @@ def main():
         return dt, n_tok, wall
 
     for i in range(args.warmup):
-        step(dev_ptrs, check=(i == 0))  # untimed: every window of the first warm-up pass is checked
+        step("dev", check=(i == 0))  # untimed: every window of the first warm-up pass is checked
     eng.stats(reset=True)
     clocks = ClockSampler(local_rank)
     if rank == 0:  # one sampler per job: the line reports rank 0's GPU, and nvidia-smi polling is not free
         clocks.start()
-    dt, n_tok, wall = timed(dev_ptrs, args.steps)
+    dt, n_tok, wall = timed("dev", args.steps)
     st = eng.stats(reset=True)
-    dt_e2e, _, wall_e2e = timed(host_ptrs, args.steps)
+    dt_e2e, _, wall_e2e = timed("host", args.steps)
     st_e2e = eng.stats(reset=True)
     clk = clocks.stop()
 
-    audio_s = 30.0 * W * world * args.steps
+    audio_local = float(sum(n_samp)) / 16000.0
+    audio_all = audio_local
+    if world > 1:
+        t = torch.tensor([audio_local], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        audio_all = float(t.item())
+    audio_s = audio_all * args.steps
     value = audio_s / dt
     e2e = audio_s / dt_e2e
     pk = peaks()
@@ -311,29 +386,32 @@ def main():
     xa_gbs = xa_bytes / (xa_ms * 1e-3) / 1e9 if xa_ms > 0 else 0.0
     enc_tf = flops_win * st["n_windows"] / (st["ms_encode"] * 1e-3) / 1e12 if st["ms_encode"] > 0 else 0.0
     dec_gbs = st["decode_bytes"] / (st["ms_decode"] * 1e-3) / 1e9 if st["ms_decode"] > 0 else 0.0
+    pcm_bytes = float(sum(n_samp)) * 2
 
     line = dict(
         metric="audio-sec/sec (RTFx)", value=value, unit="audio-sec/sec", n_gpus=world,
         steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * dt / args.steps,
         host_ms_per_step=1e3 * wall / args.steps,
         timing="CUDA events around the K steps, max over ranks (host clock of the same region: host_ms_per_step)",
-        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16 (f32 accumulate)",
+        higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="bf16 (f32 accumulate)",
         data="synthetic",
-        config=dict(workload="whisper %s greedy batch-%d, %d x 30 s windows per GPU per step "
-                             "(BASELINE configs[4] share of one GPU)" % (args.model, args.batch, W),
-                    windows_per_gpu=W, batch=args.batch, script_tokens=args.script_len,
-                    params="SttEngine defaults: greedy, token_timestamps, suppress_nst, temperature_inc 0.2",
+        config=dict(workload=cfg["what"], baseline_config=args.config, model=args.model,
+                    windows_per_gpu=W, batch=args.batch, beam=beam, script_tokens=args.script_len,
+                    audio_seconds_per_step=audio_all,
+                    params="SttEngine defaults: %s, token_timestamps, suppress_nst, temperature_inc 0.2" %
+                           ("beam search (5 beams)" if beam > 1 else "greedy (best_of 5)"),
                     lanes="%d lanes (batches in flight) x batch %d" % (lanes, args.batch),
-                    host_threads=int(params.n_threads),
+                    host_threads=int(n_threads),
                     l2="per-step working set (cross-KV %.1f GB) exceeds the 126 MB L2" %
-                       (Ld * 2 * 1500 * d * 2 * args.batch / 1e9)),
+                       (Ld * 2 * 1500 * d * 2 * min(args.batch, W) / 1e9)),
         e2e=dict(value=e2e, unit="audio-sec/sec",
                  h2d_bytes_per_step=int(st_e2e["h2d_bytes"] / args.steps),
                  d2h_bytes_per_step=int(st_e2e["d2h_bytes"] / args.steps)),
         gpu_launches=int(st["n_launches"]),
         parity_check=dict(parity, distinct_transcripts=len(seen),
-                          note="greedy token ids of every window of one pass vs the transcript its own clip spells "
-                               "(keyed model: 85 of the ~93 tokens per window are chosen by the audio)"),
+                          note="token ids of every window of one pass vs the transcript its own clip spells "
+                               "(keyed model: most tokens of a window are chosen by the audio; clips shorter than 30 s "
+                               "are compared up to the first timestamp past their end)"),
         clocks=clk,
         roofline=dict(bound="hbm", kernel="cross_attention_kernel", achieved=xa_gbs, peak=pk["hbm"],
                       unit="GB/s", frac=xa_gbs / pk["hbm"],
@@ -355,20 +433,23 @@ def main():
             decode_steps=int(st["n_steps"] / args.steps),
             device_ms_per_step=dict(mel=st["ms_mel"] / args.steps, encode=st["ms_encode"] / args.steps,
                                     decode=st["ms_decode"] / args.steps),
-            frontend_gbs=(480000 * 2 + nm * 3000 * 4) * W * args.steps / max(1e-9, st["ms_mel"] * 1e-3) / 1e9,
+            frontend_gbs=(pcm_bytes + nm * 3000 * 4 * W) * args.steps / max(1e-9, st["ms_mel"] * 1e-3) / 1e9,
             frontend_note="(int16 PCM in + f32 log-mel out) / device time of the front end (mel + token-timestamp energy kernels, uploads)",
             encoder_ms_per_window=st["ms_encode"] / max(1, st["n_windows"]),
             encoder_tflops=enc_tf, encoder_frac_of_sustained_peak=enc_tf / pk["tf_sust"],
             decode_gbs=dec_gbs, decode_frac_of_hbm=dec_gbs / pk["hbm"]))
 
+    def clip_i16(w):
+        return host_np[offs[w]:offs[w + 1]]
+
     # ---- prosody row: every window cut into six 5 s segments, through the C ABI
     # with host int16 buffers (upload inside the timed region), next to the reference's own host code
-    if rank == 0:
+    if rank == 0 and args.config == 5:
         segs = [(k * 80000, (k + 1) * 80000) for k in range(6)]
-        eng.prosody_segments(host_np[0], segs)
+        eng.prosody_segments(clip_i16(0), segs)
         t0 = time.perf_counter()
         for i in range(W):
-            eng.prosody_segments(host_np[i], segs)
+            eng.prosody_segments(clip_i16(i), segs)
         dtp = time.perf_counter() - t0
         line["stages"]["prosody"] = dict(
             gpu_audio_s_per_s=30.0 * W / dtp, ms_per_window=1e3 * dtp / W, segments_per_window=6,
@@ -379,7 +460,7 @@ def main():
             impl = pro.reference()
             kind = "reference" if impl is not None else "port"
             impl = impl or pro.oracle()
-            f32 = synth_audio.to_f32(host_np[0])
+            f32 = synth_audio.to_f32(clip_i16(0))
             t0 = time.perf_counter()
             for a, b in segs:
                 impl.extract(f32[a:b])
@@ -397,37 +478,75 @@ def main():
         from oracle import ora
         cores = os.cpu_count() or 1
         o = ora.Oracle(path, weight_round=False, act_round=ora.ACT_F16, threads=cores)
-        po = o.default_params(0, **SERVICE_PARAMS)
-        n_ora = max(1, args.oracle_windows)
-        t_all, same = 0.0, 0
+        n_ora = max(1, min(W, args.oracle_windows))
+        t_all, same, a_all = 0.0, 0, 0.0
         for w in range(n_ora):
-            pcm = synth_audio.to_f32(host_np[w])
+            lg = langs[mine[w] % len(langs)]
+            kw = dict(SERVICE_PARAMS, language=lg)
+            po = o.default_params(1, beam_size=beam, **kw) if beam > 1 else o.default_params(0, **kw)
+            pcm = synth_audio.to_f32(clip_i16(w))
             t0 = time.perf_counter()
             r = o.full(pcm, po)
             t_all += time.perf_counter() - t0
+            a_all += len(pcm) / 16000.0
             ids = [t["id"] for sg in r["segments"] for t in sg["tokens"]]
             same += int(ids == got_ids.get(w))
         line["parity_check"]["oracle_windows"] = n_ora
         line["parity_check"]["token_identical_to_oracle"] = same
         line["cpu_baseline"] = dict(
-            value=30.0 * n_ora / t_all, unit="audio-sec/sec", cores=cores, kind="port",
-            sample="%d of the %d windows (30 s audio each), %.1f s of CPU; CPU restatement of whisper.cpp "
-                   "v1.8.2, not ggml" % (n_ora, W, t_all))
+            value=a_all / t_all, unit="audio-sec/sec", cores=cores, kind="port",
+            sample="%d of the %d windows (%.0f s of audio), %.1f s of CPU; CPU restatement of whisper.cpp "
+                   "v1.8.2, not ggml" % (n_ora, W, a_all, t_all))
         if cores > 4:
             o.set_threads(4)
+            po = o.default_params(1, beam_size=beam, **dict(SERVICE_PARAMS, language=langs[mine[0] % len(langs)])) \
+                if beam > 1 else o.default_params(0, **dict(SERVICE_PARAMS, language=langs[mine[0] % len(langs)]))
             t0 = time.perf_counter()
-            o.full(synth_audio.to_f32(host_np[0]), po)
+            o.full(synth_audio.to_f32(clip_i16(0)), po)
             dt4 = time.perf_counter() - t0
             line["cpu_baseline"]["n_threads_4"] = dict(
-                value=30.0 / dt4, cores=4, sample="1 window with the reference's default n_threads = 4 (config.h:40), %.1f s" % dt4)
+                value=n_samp[0] / 16000.0 / dt4, cores=4,
+                sample="1 window with the reference's default n_threads = 4 (config.h:40), %.1f s" % dt4)
         o.close()
+    eng.close()
+    if rank == 0 and world == 1 and args.facade:
+        line["e2e_facade"] = run_facade(args, path, host_np, offs, n_samp, beam, langs[0])
     if rank == 0:
         print(json.dumps(line), flush=True)
-    eng.close()
     L.sw_host_free(host)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_facade(args, path, host_np, offs, n_samp, beam, lang):
+    """The reference-facing front door under load: W caller threads, each handing its own
+    clip to SttEngine::transcribe_pcm16 as a pageable std::vector (what the HTTP / gRPC handlers do,
+    http_server.cpp:165, grpc_server.cpp:58), parallel_requests = W, batched by the facade's dispatcher.
+    Runs host/build/stt_cli in its `bench` mode (separate process: the engine above is closed first)."""
+    W = len(n_samp)
+    clip = max(n_samp)
+    raw = "/tmp/sw_bench_facade_%d.raw" % os.getpid()
+    buf = np.zeros((W, clip), np.int16)
+    for w in range(W):
+        buf[w, : n_samp[w]] = host_np[offs[w]:offs[w + 1]]
+    buf.tofile(raw)
+    cli = os.path.join(PKG, "host", "build", "stt_cli")
+    cmd = [cli, os.path.dirname(path), os.path.basename(path), raw, str(W), str(beam), "bench", "16000",
+           "max_batch=%d" % args.batch, "steps=%d" % args.steps, "warmup=1", "clip=%d" % clip,
+           "language=%s" % lang, "batch_window_us=20000"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+        os.unlink(raw)
+        if r.returncode != 0:
+            return dict(error=(r.stderr or r.stdout)[-300:])
+        o = json.loads(r.stdout.strip().splitlines()[-1])
+        return dict(value=o["audio_s_per_s"], unit="audio-sec/sec", callers=o["callers"], ms_per_step=o["ms_per_step"],
+                    device_passes=o["device_passes"], failures=o["failures"], tokens=o["tokens"],
+                    note="SttEngine::transcribe_pcm16 from %d caller threads, pageable std::vector<int16_t> input, "
+                         "results as TranscriptionResult vectors incl. prosody + speaker ids; host clock" % W)
+    except Exception as ex:  # the facade leg must not take the bench line down
+        return dict(error=str(ex)[-300:])
 
 
 if __name__ == "__main__":

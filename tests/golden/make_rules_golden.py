@@ -12,7 +12,8 @@ decoding.py rules that whisper.cpp also ports), and `WhisperForConditionalGenera
 What is produced (all driven by HF code only; the oracle is compared against it in
 tests/test_oracle_vs_hf_rules.py, which also re-runs HF live when transformers is importable):
   * for N seeded (logits, token history) cases: the -inf mask HF's three processors leave, as packed bits;
-  * HF greedy `generate(return_timestamps=True)` token sequences on the micro model for 3 clips.
+  * HF greedy `generate(return_timestamps=True)` token sequences on the keyed micro model (tools/gen_model.py
+    --keyed: the audio chooses the text tokens) for 3 clips that spell different symbol sequences.
 
 Intentional, NAMED differences between whisper.cpp (as restated by the oracle) and HF/OpenAI:
   D1 initial_text_not_forced : OpenAI/HF suppress every non-timestamp token at the first sampled position;
@@ -36,7 +37,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from tools import gen_model, ggml_io, synth_audio  # noqa: E402
 
-MODEL_ARGS = dict(size="micro", seed=1234, script_len=40)
+MODEL_ARGS = dict(size="micro", seed=1234, script_len=40, keyed=4)  # a model that listens: every clip, its own tokens
 N_CASES = 96
 NON_SPEECH = gen_model.NON_SPEECH
 
@@ -150,6 +151,11 @@ def hf_generate(m, sp, mel_window, max_new=60):
     return seq
 
 
+def golden_clip(info, i):
+    k = info["keyed"]
+    return synth_audio.keyed_clip(k, synth_audio.keyed_symbols(k, 900 + i), seed=900 + i)
+
+
 def main():
     from make_golden import hf_model
     from oracle import ora
@@ -172,8 +178,11 @@ def main():
     o = ora.Oracle(path, weight_round=False, act_round=ora.ACT_F32, gelu_erf=True)
     seqs = []
     for i in range(3):
-        mel, _ = o.mel(synth_audio.to_f32(synth_audio.utterance(1, i)))
+        mel, _ = o.mel(synth_audio.to_f32(golden_clip(info, i)))
         seq = hf_generate(m, sp, mel[:, :3000])
+        want = gen_model.keyed_expected_tokens(info, synth_audio.keyed_symbols(info["keyed"], 900 + i))
+        kept = [t for j, t in enumerate(seq) if t != sp["eot"] and not (j > 0 and t >= sp["beg"] and seq[j - 1] == t)]
+        assert kept == want, "HF does not read clip %d's symbols back" % i
         print("hf generate clip %d: %d tokens, head %s" % (i, len(seq), seq[:8]))
         seqs.append(np.array(seq, np.int32))
     n = max(len(s) for s in seqs)

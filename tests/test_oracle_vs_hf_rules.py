@@ -24,7 +24,7 @@ def ctx(ora):
     g = np.load(os.path.join(HERE, "golden", "rules_hf.npz"))
     args = ast.literal_eval(str(g["model_args"]))
     assert args == mrg.MODEL_ARGS
-    path, info = model_file(args["size"], seed=args["seed"], script_len=args["script_len"])
+    path, info = model_file(args["size"], seed=args["seed"], script_len=args["script_len"], keyed=args["keyed"])
     hp, _, vocab, _ = ggml_io.read_ggml(path)
     o = ora.Oracle(path)
     return dict(g=g, path=path, info=info, sp=info["special"], vocab=vocab, n_vocab=hp["n_vocab"], o=o)
@@ -149,5 +149,6 @@ def test_greedy_sequence_matches_hf_generate_golden(ctx, ora):
         if seq[: len(g["prompt"])] == g["prompt"].tolist():
             seq = seq[len(g["prompt"]):]
         kept = [t for j, t in enumerate(seq) if t != sp["eot"] and not (j > 0 and t >= sp["beg"] and seq[j - 1] == t)]
-        r = o.full(synth_audio.to_f32(synth_audio.utterance(1, i)), p)
+        r = o.full(synth_audio.to_f32(mrg.golden_clip(ctx["info"], i)), p)
         assert seg_ids(r) == kept
+    assert len({tuple(int(t) for t in row) for row in g["hf_sequences"]}) == 3  # three clips, three transcripts

@@ -253,6 +253,25 @@ def keyed_expected_tokens(info, symbols):
     return [t for i, t in enumerate(script[:-1]) if not (i > 0 and t >= beg and script[i - 1] == t)]
 
 
+def keyed_sure_prefix(info, n_samples, guard=3200):
+    """How many of keyed_expected_tokens() a clip cut to n_samples (16 kHz) still decides: up to the first text
+    token whose tone slot is not wholly inside the audio (minus a 0.2 s guard) or the first timestamp past its end."""
+    k = info["keyed"]
+    script, beg = info["script"], info["special"]["beg"]
+    slot_of = {si: k["slots"][i] for i, si in enumerate(k["text_index"])}
+    kept = 0
+    for i, t in enumerate(script[:-1]):
+        if i > 0 and t >= beg and script[i - 1] == t:
+            continue
+        if i in slot_of:
+            if slot_of[i][1] * 320 > n_samples - guard:
+                return kept
+        elif t >= beg and (t - beg) * 320 > n_samples:
+            return kept
+        kept += 1
+    return kept
+
+
 class GgmlWriter:
     def __init__(self, path):
         self.f = open(path, "wb")
@@ -277,7 +296,7 @@ class GgmlWriter:
 
 def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, ln_f_gain=None,
              script_end_cs=3000, w_std=0.02, emb_std=0.02, f32_all=False, verbose=False,
-             script_final_pair=False, script_first_ts=0, keyed=0, keyed_beta=0.6, keyed_delta=1.2, keyed_attn=2.5,
+             script_final_pair=False, script_first_ts=0, keyed=0, keyed_beta=1.2, keyed_delta=0.6, keyed_attn=1.5,
              keyed_gain=0.7):
     d, n_head, n_layer, n_mel, n_vocab = SIZES[size]
     if seed is None:
@@ -443,8 +462,11 @@ def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, l
             keyed_info = dict(K=K, variants=variants, slots=slots, text_index=text_index,
                               tones_hz=[keyed_tone_hz(k) for k in range(K)])
             # keyed_beta is relative: the band term written into the stream has about keyed_beta times the
-            # norm of the scripted term (band values after ln_post, offset removed: ~2 active, 0 idle)
-            kp["beta"] = keyed_beta * script_rms * np.sqrt(d) / 2.0
+            # norm of the scripted term. An active band reads ~1.29 / sigma_t after ln_post (idle: 0), where
+            # sigma_t^2 ~ 0.2 + 0.036 L is the encoder stream's variance (measured on the oracle, L = 2 .. 24);
+            # the mean-free value vector has sqrt(3/4) of that norm
+            sigma_t = np.sqrt(0.2 + 0.036 * n_layer)
+            kp["beta"] = keyed_beta * script_rms * np.sqrt(d) / (1.29 / sigma_t * np.sqrt(1.0 - 1.0 / K))
             extra_var = (J * 1.0) / d + (keyed_beta * script_rms) ** 2
         else:
             script = make_script(sp, script_len, seed + 2, n_base - 1, end_cs=script_end_cs,
@@ -476,7 +498,10 @@ def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, l
 
     def alignment_head(t):
         # head 0 (rows / columns 0..63) of the last layer's cross attention
-        J, a = kp["J"], np.float32(keyed_attn)
+        # score(p, t) = a^2 / 8 * sum_r q_r k_r / (sigma' sigma_t) = s * sum_j cos(omega_j (t - tau_p)): the sharpness s
+        # (keyed_attn) is kept the same for every depth by scaling a with the two LayerNorm divisors
+        sigma_q = np.sqrt(script_rms ** 2 + 0.04 * n_layer + extra_var)
+        J, a = kp["J"], np.float32(np.sqrt(8.0 * keyed_attn * sigma_q * np.sqrt(0.2 + 0.036 * n_layer)))
         for name in ("qw", "kw", "vw"):
             t[name][:64] = 0.0
         t["qb"][:64] = 0.0
@@ -488,9 +513,11 @@ def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, l
             t["qw"][r, kp["dec_zero_ch"]] = -a
             t["kw"][r, kp["enc_pos_ch"][r]] = a
             t["kw"][r, kp["enc_zero_ch"]] = -a
+        # value k = band_k - mean of the bands: zero when the head looks everywhere at once (timestamp positions,
+        # q = 0) and clips use the bands evenly; the coefficients sum to 0, so LayerNorm's offset cancels here too
         for k in range(K):
-            t["vw"][k, kp["enc_band_ch"][k]] = 1.0
-            t["vw"][k, kp["enc_zero_ch"]] = -1.0
+            for k2 in range(K):
+                t["vw"][k, kp["enc_band_ch"][k2]] = (1.0 if k == k2 else 0.0) - 1.0 / K
         t["ow"][:, :64] = 0.0
         for k in range(K):
             t["ow"][:, k] = kp["beta"] * kp["wdir"][k]

@@ -195,6 +195,10 @@ def main():
     ap.add_argument("--script-len", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--oracle-windows", type=int, default=3, help="windows the CPU oracle also transcribes (parity + cpu_baseline)")
+    ap.add_argument("--inproc", type=int, default=0,
+                    help="N > 0: ONE process, N contexts on devices 0..N-1 driven by N host threads (the in-process "
+                         "dispatcher of SURVEY.md §8(e)) instead of one process per GPU; prints the same line with "
+                         "mode=inproc")
     ap.add_argument("--facade", action="store_true",
                     help="also measure the reference-facing class: caller threads on SttEngine::transcribe_pcm16 with "
                          "pageable vectors (host/stt_cli bench mode) -> e2e_facade")
@@ -218,6 +222,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return 0
+    if args.inproc > 0:
+        return run_inproc(args, cfg)
 
     import torch
     import torch.distributed as dist
@@ -516,6 +522,106 @@ def main():
     L.sw_host_free(host)
     if world > 1:
         dist.destroy_process_group()
+    return 0
+
+
+def run_inproc(args, cfg):
+    """One process, N GPUs: a host dispatcher deals the utterances to per-GPU worker threads, each with its own
+    sw_ctx (weights replicated), streams and lanes; results come back to the caller through the threads' result
+    lists (SURVEY.md §8(e) "host dispatcher ... host-side result gather"). No collective, no torch.distributed.
+    Timed per device with CUDA events (max over devices) and with the host clock around all threads."""
+    import torch
+    N = args.inproc
+    if torch.cuda.device_count() < N:
+        raise SystemExit("bench.py --inproc %d: only %d CUDA devices" % (N, torch.cuda.device_count()))
+    from tools import synth_audio
+    disp = importlib.util.spec_from_file_location("dispatch", os.path.join(PKG, "dispatch.py"))
+    dispatch = importlib.util.module_from_spec(disp)
+    disp.loader.exec_module(dispatch)
+    path = ensure_model(args.model, args.script_len)
+    minfo = model_info(path)
+    swb = load_binding()
+    L = swb.lib()
+    L.sw_result_token_data.restype = swb.TokenData
+    W0 = int(cfg.get("windows", 128))
+    total = W0 * N
+    n_s = 480000
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
+    ptr16 = C.POINTER(C.c_int16)
+    workers = []
+    for dev in range(N):
+        eng = swb.Engine(path, device=dev, max_batch=args.batch, max_beams=5)
+        p = eng.default_params(0, **SERVICE_PARAMS)
+        p.n_threads = max(2, min(16, cores // N))
+        mine = dispatch.shard_utterances(total, N, dev)
+        host = L.sw_host_alloc(len(mine) * n_s * 2)
+        host_np = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_int16)), shape=(len(mine), n_s))
+        want = []
+        for j, i in enumerate(mine):
+            host_np[j], ids = window_clip(minfo, i)
+            want.append(ids)
+        workers.append(dict(dev=dev, eng=eng, params=p, n=len(mine), host=host, want=want,
+                            lens=(C.c_int * len(mine))(*([n_s] * len(mine))),
+                            ptrs=(ptr16 * len(mine))(*[C.cast(host + j * n_s * 2, ptr16) for j in range(len(mine))]),
+                            ok=0, dt=0.0))
+
+    def one_pass(w, check):
+        res = w["eng"].full_batch_ptrs(w["ptrs"], w["lens"], w["n"], w["params"])
+        for j, r in enumerate(res):
+            if check:
+                ids = [L.sw_result_token_data(r, s, q).id for s in range(L.sw_result_n_segments(r))
+                       for q in range(L.sw_result_n_tokens(r, s))]
+                w["ok"] += int(ids == w["want"][j])
+            L.sw_result_free(r)
+
+    start = threading.Barrier(N + 1)
+
+    def worker(w, k, check):
+        torch.cuda.set_device(w["dev"])
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        start.wait()
+        ev0.record()
+        for _ in range(k):
+            one_pass(w, check)
+        ev1.record()
+        torch.cuda.synchronize()
+        w["dt"] = ev0.elapsed_time(ev1) * 1e-3
+
+    def run(k, check=False):
+        th = [threading.Thread(target=worker, args=(w, k, check)) for w in workers]
+        for t in th:
+            t.start()
+        start.wait()
+        t0 = time.perf_counter()
+        for t in th:
+            t.join()
+        return time.perf_counter() - t0, max(w["dt"] for w in workers)
+
+    run(1, check=True)
+    if args.warmup > 1:
+        run(args.warmup - 1)
+    clocks = ClockSampler(0)
+    clocks.start()
+    wall, dt = run(args.steps)
+    clk = clocks.stop()
+    h2d = sum(w["eng"].stats(reset=True)["h2d_bytes"] for w in workers)
+    audio_s = 30.0 * total * args.steps
+    line = dict(metric="audio-sec/sec (RTFx)", mode="inproc", value=audio_s / dt, unit="audio-sec/sec", n_gpus=N,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * dt / args.steps,
+                host_ms_per_step=1e3 * wall / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="bf16 (f32 accumulate)", data="synthetic",
+                timing="CUDA events per device around its K passes, max over devices (host clock: host_ms_per_step)",
+                config=dict(workload=cfg["what"] + "; ONE process, %d contexts / host threads (in-process dispatcher), "
+                                     "host PCM in pinned memory" % N, model=args.model, windows_per_gpu=W0, batch=args.batch),
+                e2e=dict(value=audio_s / dt, unit="audio-sec/sec", h2d_bytes_per_step=int(h2d / (args.steps + args.warmup)),
+                         note="inputs are host buffers in this mode: value is end to end"),
+                parity_check=dict(windows=total, token_identical_to_expected=sum(w["ok"] for w in workers)),
+                clocks=clk)
+    print(json.dumps(line), flush=True)
+    for w in workers:
+        w["eng"].close()
+        L.sw_host_free(w["host"])
     return 0
 
 

@@ -635,3 +635,31 @@ def test_config5_large_v3_batch64_properties(swb, ora):
     st = e.stats()
     assert st["n_lanes"] == 2 and st["n_windows"] == 72
     e.close()
+
+
+def test_two_devices_in_one_process(swb, ora):
+    """the per-kernel shared-memory opt-in and the SM count are per DEVICE. Two contexts on
+    two GPUs of one process (as INTEGRATION.md's "one SttEngine per GPU" deployment creates them), driven from
+    two host threads at once, return what a single context returns."""
+    import threading
+    if swb.lib().sw_device_count() < 2:
+        pytest.skip("needs two sm_100 devices")
+    path, info = model_file("tiny", script_len=40, keyed=4)
+    k = info["keyed"]
+    clips = [synth_audio.keyed_clip(k, synth_audio.keyed_symbols(k, s), seed=s) for s in range(80, 92)]
+    e1 = swb.Engine(path, device=1, max_batch=8)   # device 1 FIRST: nothing has been opted in on it by device 0
+    e0 = swb.Engine(path, device=0, max_batch=8)
+    outs = {}
+
+    def work(name, e, part):
+        outs[name] = e.full_batch_pcm16(part, e.default_params(0, **GREEDY))
+    th = [threading.Thread(target=work, args=("a", e0, clips[:6])), threading.Thread(target=work, args=("b", e1, clips[6:]))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    both = e0.full_batch_pcm16(clips, e0.default_params(0, **GREEDY))
+    for got, want in zip(outs["a"] + outs["b"], both):
+        compare_results(got, want)
+    e0.close()
+    e1.close()

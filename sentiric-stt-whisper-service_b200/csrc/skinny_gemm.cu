@@ -50,7 +50,7 @@ template <int BN>
 struct SkCfg {
   static constexpr int W_BYTES = BN * SK_BK * 2;
   static constexpr int STAGE_BYTES = SK_X_BYTES + W_BYTES;  // 12 / 13 KB: stage bases stay 1024-byte aligned
-  static constexpr int SMEM = SK_STAGES * STAGE_BYTES + 1024 + 2 * SK_STAGES * 8;
+  static constexpr int smem(int n_stages) { return n_stages * STAGE_BYTES + 1024 + 2 * n_stages * 8; }
   static constexpr int NT = BN / 8;        // 8-column MMA tiles of the CTA
   static constexpr int NT0 = (NT + 1) / 2;  // tiles of column-warp 0 (column-warp 1 takes the rest)
 };
@@ -59,13 +59,13 @@ template <int BN>
 __global__ void __launch_bounds__(SK_THREADS, 2)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, int R,
                    int N, int k_slice, const float* __restrict__ bias, int gelu, bf16* __restrict__ out, int ldo,
-                   float* __restrict__ partial, uint32_t zero) {
+                   float* __restrict__ partial, uint32_t zero, int n_stages) {
   using C = SkCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t sbase = smem_u32(smem);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SK_STAGES * C::STAGE_BYTES);
-  uint64_t* empty = full + SK_STAGES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + n_stages * C::STAGE_BYTES);
+  uint64_t* empty = full + n_stages;
   const int n0 = blockIdx.x * BN;
   const int k_begin = blockIdx.y * k_slice;
   const int r0 = blockIdx.z * SK_BM;
@@ -76,7 +76,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (tid == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
-    for (int s = 0; s < SK_STAGES; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], SK_CONSUMERS);
     }
@@ -89,7 +89,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // the active lanes (R2UR + ELECT + BRA.U.ANY around every UTMALDG)
     if (elect_one_sync()) {
       // weights first (independent of the predecessor), activations once it has finished
-      const int pre = n_kb < SK_STAGES ? n_kb : SK_STAGES;
+      const int pre = n_kb < n_stages ? n_kb : n_stages;
       for (int kb = 0; kb < pre; ++kb) {
         mbar_arrive_expect_tx(&full[kb], C::STAGE_BYTES);
         tma_load_2d(smem + kb * C::STAGE_BYTES + SK_X_BYTES, &map_w, &full[kb], k_begin + kb * SK_BK, n0);
@@ -98,8 +98,8 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       for (int kb = 0; kb < pre; ++kb)
         tma_load_2d(smem + kb * C::STAGE_BYTES, &map_x, &full[kb], k_begin + kb * SK_BK, r0);
       for (int kb = pre; kb < n_kb; ++kb) {
-        const int s = kb % SK_STAGES;
-        const uint32_t ph = (kb / SK_STAGES) & 1;
+        const int s = kb % n_stages;
+        const uint32_t ph = (kb / n_stages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
         uint8_t* xs = smem + s * C::STAGE_BYTES;
@@ -124,8 +124,8 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const int b_row4 = t0 * 8 + (lane & 7) + (lane >> 4) * 8;
   const int b_ch = (lane >> 3) & 1;
   for (int kb = 0; kb < n_kb; ++kb) {
-    const int s = kb % SK_STAGES;
-    const uint32_t ph = (kb / SK_STAGES) & 1;
+    const int s = kb % n_stages;
+    const uint32_t ph = (kb / n_stages) & 1;
     mbar_wait(&full[s], ph);
     const uint32_t xs = sbase + s * C::STAGE_BYTES, ws = xs + SK_X_BYTES;
     uint32_t a[SK_BK / 16][4], b[SK_BK / 16][C::NT0][2];
@@ -227,9 +227,17 @@ int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, cons
   SW_CHECK(partial || out, "skinny_gemm: null output");
   SW_CHECK((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
            "skinny_gemm: operands must be 16-byte aligned");
+  // ring depth: 8 stages (two CTAs of ~100 KB per SM) when the launch has the GPU to itself; SW_SKINNY_STAGES
+  // selects a shallower ring (development: 4 stages = 53 KB, small enough to share an SM with a resident
+  // cross-attention CTA of the other lane)
+  static const int n_stages = [] {
+    const char* v = getenv("SW_SKINNY_STAGES");
+    const int n = v ? atoi(v) : SK_STAGES;
+    return n >= 2 && n <= SK_STAGES ? n : SK_STAGES;
+  }();
   static SmemOptIn opt_in32, opt_in40;  // per device (host_common.h)
-  SW_CUDA_CHECK(opt_in32.ensure(skinny_gemm_kernel<32>, SkCfg<32>::SMEM));
-  SW_CUDA_CHECK(opt_in40.ensure(skinny_gemm_kernel<40>, SkCfg<40>::SMEM));
+  SW_CUDA_CHECK(opt_in32.ensure(skinny_gemm_kernel<32>, SkCfg<32>::smem(SK_STAGES)));
+  SW_CUDA_CHECK(opt_in40.ensure(skinny_gemm_kernel<40>, SkCfg<40>::smem(SK_STAGES)));
   const int k_slice = K / split;
   const int row_blocks = (R + SK_BM - 1) / SK_BM;
   static const int force_bn = getenv("SW_SKINNY_BN") ? atoi(getenv("SW_SKINNY_BN")) : 0;  // development switch
@@ -239,11 +247,11 @@ int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, cons
   if (make_tma_map_2d_bf16(&map_w, W, K, N, K, SK_BK, bn)) return -1;
   dim3 grid((N + bn - 1) / bn, split, row_blocks);
   if (bn == 40)
-    SW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<40>, grid, dim3(SK_THREADS), SkCfg<40>::SMEM, stream, map_x, map_w, R,
-                             N, k_slice, bias, gelu, out, ldo, partial, 0u));
+    SW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<40>, grid, dim3(SK_THREADS), SkCfg<40>::smem(n_stages), stream, map_x,
+                             map_w, R, N, k_slice, bias, gelu, out, ldo, partial, 0u, n_stages));
   else
-    SW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<32>, grid, dim3(SK_THREADS), SkCfg<32>::SMEM, stream, map_x, map_w, R,
-                             N, k_slice, bias, gelu, out, ldo, partial, 0u));
+    SW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<32>, grid, dim3(SK_THREADS), SkCfg<32>::smem(n_stages), stream, map_x,
+                             map_w, R, N, k_slice, bias, gelu, out, ldo, partial, 0u, n_stages));
   return 0;
 }
 

@@ -295,16 +295,14 @@ def main():
         n_sure.append(len(ids) if n_samp[j] >= 480000 else gen_model.keyed_sure_prefix(minfo, n_samp[j]))
     dev = torch.from_numpy(host_np.copy()).cuda()
     ptr16 = C.POINTER(C.c_int16)
-    groups = []   # one C-ABI call per language (a call carries one sw_full_params)
-    for li, lg in enumerate(langs):
-        idx = [j for j in range(W) if mine[j] % len(langs) == li]
-        if not idx:
-            continue
-        n = len(idx)
-        groups.append(dict(
-            lang=lg, idx=idx, n=n, lens=(C.c_int * n)(*[n_samp[j] for j in idx]),
-            host=(ptr16 * n)(*[C.cast(host + int(offs[j]) * 2, ptr16) for j in idx]),
-            dev=(ptr16 * n)(*[C.cast(dev.data_ptr() + int(offs[j]) * 2, ptr16) for j in idx])))
+    # ONE C-ABI call per step: sw_full_batch_pcm16_lang carries a language per utterance (utterance i of
+    # config 4 speaks langs[i % 4]), so mixed-language work shares device passes
+    idx = list(range(W))
+    groups = [dict(
+        lang=langs[0], idx=idx, n=W, lens=(C.c_int * W)(*n_samp),
+        langs=(C.c_char_p * W)(*[langs[mine[j] % len(langs)].encode() for j in idx]) if len(langs) > 1 else None,
+        host=(ptr16 * W)(*[C.cast(host + int(offs[j]) * 2, ptr16) for j in idx]),
+        dev=(ptr16 * W)(*[C.cast(dev.data_ptr() + int(offs[j]) * 2, ptr16) for j in idx]))]
 
     L.sw_result_token_data.restype = swb.TokenData
     parity = dict(windows=0, token_identical_to_expected=0, distinct_transcripts=0)
@@ -313,7 +311,7 @@ def main():
     def step(which, check=False):
         n_tok = 0
         for g in groups:
-            res = eng.full_batch_ptrs(g[which], g["lens"], g["n"], params_by_lang[g["lang"]])
+            res = eng.full_batch_ptrs(g[which], g["lens"], g["n"], params_by_lang[g["lang"]], languages=g["langs"])
             for w, r in zip(g["idx"], res):
                 ids = []
                 for s in range(L.sw_result_n_segments(r)):

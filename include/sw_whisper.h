@@ -133,6 +133,13 @@ SW_API int sw_full_batch_pcm16(sw_ctx* ctx, const sw_full_params* params,
                                sw_result** out);
 SW_API int sw_full_batch_f32(sw_ctx* ctx, const sw_full_params* params, const float* const* pcm,
                              const int* n_samples, int n, sw_result** out);
+/* The same with a language per utterance: languages[i] is "en", "tr", ... or "auto" / NULL (detect); languages == NULL
+ * means params->language for all. The language is the one per-request setting that only changes a prompt token
+ * (stt_engine.cpp:230-232), so requests in different languages can share a device pass. */
+SW_API int sw_full_batch_pcm16_lang(sw_ctx* ctx, const sw_full_params* params, const int16_t* const* pcm16,
+                                    const int* n_samples, int n, const char* const* languages, sw_result** out);
+SW_API int sw_full_batch_f32_lang(sw_ctx* ctx, const sw_full_params* params, const float* const* pcm,
+                                  const int* n_samples, int n, const char* const* languages, sw_result** out);
 /* page-locked host memory for PCM staging (optional; any host pointer is accepted) */
 SW_API void* sw_host_alloc(size_t bytes);
 SW_API void sw_host_free(void* p);

@@ -1,4 +1,4 @@
-// Route B driver: built ONLY by oracle/Makefile (target routeb) together with the reference's own, unmodified
+// Route B driver (test infrastructure): built by this directory's Makefile (target routeb) together with the reference's own, unmodified
 // stt_engine.cpp / prosody_extractor.cpp / speaker_cluster.cpp. It includes the REFERENCE's stt_engine.h and
 // uses nothing but the reference's public API; the JSON it prints has the layout of host/stt_cli.cpp's batch
 // mode, so a test can hold the two facades side by side on the same clip.

@@ -150,6 +150,30 @@ int sw_full_batch_pcm16(sw_ctx* ctx, const sw_full_params* params, const int16_t
   API_GUARD_END(-1)
 }
 
+int sw_full_batch_pcm16_lang(sw_ctx* ctx, const sw_full_params* params, const int16_t* const* pcm16,
+                             const int* n_samples, int n, const char* const* languages, sw_result** out) {
+  API_GUARD_BEGIN
+  if (!ctx || !params || !pcm16 || !n_samples || !out) {
+    set_last_error("null argument");
+    return -1;
+  }
+  return sw::run_full_batch_lanes(ctx, params, reinterpret_cast<const void* const*>(pcm16), n_samples, n, false, out,
+                                  languages);
+  API_GUARD_END(-1)
+}
+
+int sw_full_batch_f32_lang(sw_ctx* ctx, const sw_full_params* params, const float* const* pcm, const int* n_samples,
+                           int n, const char* const* languages, sw_result** out) {
+  API_GUARD_BEGIN
+  if (!ctx || !params || !pcm || !n_samples || !out) {
+    set_last_error("null argument");
+    return -1;
+  }
+  return sw::run_full_batch_lanes(ctx, params, reinterpret_cast<const void* const*>(pcm), n_samples, n, true, out,
+                                  languages);
+  API_GUARD_END(-1)
+}
+
 int sw_full_batch_f32(sw_ctx* ctx, const sw_full_params* params, const float* const* pcm,
                       const int* n_samples, int n, sw_result** out) {
   API_GUARD_BEGIN

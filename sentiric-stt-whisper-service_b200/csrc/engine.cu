@@ -35,6 +35,7 @@ Engine::~Engine() {
     if (ev) cudaEventDestroy(ev);
   engine_free_step_graphs(this);
   if (stream) cudaStreamDestroy(stream);
+  if (post_stream) cudaStreamDestroy(post_stream);
   if (owns_model) delete model;
 }
 
@@ -71,6 +72,7 @@ static int engine_init(Engine* e, const char* path, const sw_ctx_params* p, cons
   }
   cudaMemGetInfo(&free0, &total0);
   SW_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  SW_CUDA_CHECK(cudaStreamCreateWithFlags(&e->post_stream, cudaStreamNonBlocking));
   SW_CUDA_CHECK(cudaEventCreate(&e->ev0));
   SW_CUDA_CHECK(cudaEventCreate(&e->ev1));
   e->xa_ev.assign(2 * (size_t)64, nullptr);

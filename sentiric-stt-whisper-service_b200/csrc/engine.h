@@ -77,12 +77,21 @@ struct Engine {
   DevBuf<MelUtt> d_utts;
   DevBuf<unsigned> d_max_enc;
   DevBuf<int> d_win_utt, d_win_seek;
-  DevBuf<float> d_energy;       // token-timestamp signal energy, same offsets as the PCM
-  PinBuf<float> h_energy;
+  DevBuf<float> d_energy;       // token-timestamp signal energy, same offsets as the PCM; never leaves HBM
   DevBuf<float> d_eblk;         // per 256-sample block min | max of the energy (two halves)
-  PinBuf<float> h_eblk;
   size_t eblk_capacity = 0;
   size_t energy_capacity = 0;
+  // token-time refinement of a finished batch (token_times.cu), on its own stream: it runs from the host
+  // thread that post-processes batch i while the main stream already decodes batch i + 1
+  cudaStream_t post_stream = nullptr;
+  DevBuf<TtSeg> d_tt_seg;
+  PinBuf<TtSeg> h_tt_seg;
+  DevBuf<long long> d_tt_t;     // t0 | t1 (two halves of tt_tok_capacity)
+  PinBuf<long long> h_tt_t;
+  DevBuf<uint8_t> d_tt_flag;
+  PinBuf<uint8_t> h_tt_flag;
+  DevBuf<float> d_tt_thold;
+  size_t tt_seg_capacity = 0, tt_tok_capacity = 0;
   int utt_capacity = 0;
   // ---- encoder activations (max_batch windows)
   DevBuf<bf16> conv_in, h1, hb, qkv, ff;

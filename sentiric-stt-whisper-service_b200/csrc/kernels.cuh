@@ -49,6 +49,20 @@ int mel_f32_to_conv_input(const float* d_mel, int n_win, int n_mel, bf16* out, c
 int signal_energy(const void* pcm, int is_f32, const MelUtt* d_utts, int n_utts, int max_n, int hw,
                   float* out, float* blk_min, float* blk_max, cudaStream_t stream);
 
+// ------------------------------------------------------------------ token-level timestamps (token_times.cu)
+struct TtSeg {            // one result segment whose tokens' [t0, t1] are refined on the signal energy
+  long long en_off;       // element offset of its utterance in the energy buffer (= MelUtt::pcm_off)
+  int blk_off;            // offset of the utterance's 256-sample blocks in the block min / max arrays
+  int n_samples;          // samples of the utterance
+  int tok_off;            // first token of the segment in the token arrays
+  int n_tok;              // its tokens (text and others; only text tokens are refined)
+};
+static_assert(sizeof(TtSeg) == 24, "TtSeg is uploaded as is");
+// t0 / t1: centiseconds, in and out; is_text: token id < eot; thold: scratch, one float per token
+int token_time_refine(const float* d_energy, const float* d_blk_min, const float* d_blk_max, const TtSeg* d_segs,
+                      int n_segs, long long* d_t0, long long* d_t1, const uint8_t* d_is_text, float* d_thold,
+                      cudaStream_t stream);
+
 // ------------------------------------------------------------------ elementwise (elementwise.cu)
 // y = LN(x) * g + b over rows of d (eps 1e-5, f32 statistics). out_bf16/out_f32 may be null.
 // If partial != null: x += bias + sum_{s<n_split} partial[s][row][:] first (split-K reduce + residual).

@@ -48,9 +48,8 @@ struct Utt {
   int seek = 0, seek_end = 0;
   std::vector<int> prompt_past;
   std::mt19937 rng[8];
-  const float* energy = nullptr;  // smoothed |x| (pinned host buffer of the engine)
-  const float* en_bmin = nullptr;  // min / max of every 256-sample block of it
-  const float* en_bmax = nullptr;
+  int64_t en_off = 0;  // its smoothed |x| in the engine's device energy buffer (same offset as its PCM)
+  int blk_off = 0;     // its 256-sample blocks in the block min / max arrays
   int n_energy = 0;
   int64_t t_beg = 0, t_last = 0;
   int tid_last = 0;
@@ -69,6 +68,7 @@ struct Window {  // one job in flight
   Decoder dec[8];
   float no_speech_prob = 0.f;
   bool done = false;  // all decoders completed or failed
+  std::vector<int> tt_segs;  // result segments this window emitted whose token times still need the energy pass
 };
 
 // ---- paged self-KV bookkeeping (host): page tables with reference counts ------------------
@@ -169,17 +169,18 @@ float voice_length(const std::string& text) {
 inline int ts_to_sample(int64_t t, int n) { return std::max(0, std::min(n - 1, (int)((t * SR) / 100))); }
 inline int64_t sample_to_ts(int i) { return (100ll * i) / SR; }
 
-void token_timestamps(const Model& m, Utt& u, sw_segment& seg) {
+// first half of whisper_exp_compute_token_level_timestamps; returns true if the segment needs the energy pass
+bool token_timestamps(const Model& m, Utt& u, sw_segment& seg) {
   const float thold_pt = 0.01f, thold_ptsum = 0.01f;
   auto& tk = seg.tokens;
   const int n_samples = u.n_energy;
   const int n = (int)tk.size();
-  if (n_samples == 0 || n == 0) return;
+  if (n_samples == 0 || n == 0) return false;
   const int64_t t0 = seg.t0, t1 = seg.t1;
   if (n == 1) {
     tk[0].t0 = t0;
     tk[0].t1 = t1;
-    return;
+    return false;
   }
   const int beg = m.vocab.beg;
   for (int j = 0; j < n; ++j) {
@@ -233,60 +234,9 @@ void token_timestamps(const Model& m, Utt& u, sw_segment& seg) {
       tk[j].t1 = std::max(tk[j].t0, tk[j].t1);
     }
   }
-  // expand / contract on the smoothed signal energy. The four threshold scans below are upstream's
-  // sample-by-sample while loops; with speech-like audio one of them can run over most of the utterance
-  // for every token (10 ms of host time per window). They step over a whole 256-sample block when the
-  // block's min (max) proves that every sample of it passes the loop condition: same result, exactly.
-  const float* en = u.energy;
-  const float *bmin = u.en_bmin, *bmax = u.en_bmax;
-  const int hw = SR / 8;
-  for (int j = 0; j < n; ++j) {
-    if (tk[j].id >= m.vocab.eot) continue;
-    int s0 = ts_to_sample(tk[j].t0, n_samples), s1 = ts_to_sample(tk[j].t1, n_samples);
-    const int ss0 = std::max(s0 - hw, 0), ss1 = std::min(s1 + hw, n_samples);
-    const int ns = ss1 - ss0;
-    float sum = 0.f;
-    for (int k = ss0; k < ss1; ++k) sum += en[k];
-    const float thold = 0.5f * sum / ns;
-    {
-      int k = s0;
-      if (en[k] > thold && j > 0) {
-        while (k > 0 && en[k] > thold) {
-          if (bmin[k >> 8] > thold) k = (k >> 8) << 8;  // every sample down to the block start is above
-          if (k > 0) k--;
-        }
-        tk[j].t0 = sample_to_ts(k);
-        if (tk[j].t0 < tk[j - 1].t1) tk[j].t0 = tk[j - 1].t1;
-        else s0 = k;
-      } else {
-        while (en[k] < thold && k < s1) {
-          if (bmax[k >> 8] < thold) k = std::min(s1, ((k >> 8) + 1) << 8);
-          else k++;
-        }
-        s0 = k;
-        tk[j].t0 = sample_to_ts(k);
-      }
-    }
-    {
-      int k = s1;
-      if (en[k] > thold) {
-        while (k < n_samples - 1 && en[k] > thold) {
-          if (bmin[k >> 8] > thold) k = std::min(n_samples - 1, (((k >> 8) + 1) << 8) - 1);
-          if (k < n_samples - 1) k++;
-        }
-        tk[j].t1 = sample_to_ts(k);
-        if (j < n - 1 && tk[j].t1 > tk[j + 1].t0) tk[j].t1 = tk[j + 1].t0;
-        else s1 = k;
-      } else {
-        while (en[k] < thold && k > s0) {
-          if (bmax[k >> 8] < thold) k = std::max(s0, ((k >> 8) << 8) - 1);
-          else k--;
-        }
-        s1 = k;
-        tk[j].t1 = sample_to_ts(k);
-      }
-    }
-  }
+  // the expand / contract of every text token on the smoothed signal energy follows on the device, for all
+  // segments of the finished batch at once (Run::refine_token_times -> token_times.cu)
+  return true;
 }
 
 // whisper_tokenize stand-in for initial_prompt: greedy longest match over the vocabulary
@@ -432,27 +382,22 @@ struct Run {
       for (int i = 0; i < n; ++i) max_n = std::max(max_n, n_samples[i]);
       if ((size_t)pcm_off > e->energy_capacity) {
         e->d_energy.release();
-        e->h_energy.release();
         e->energy_capacity = (size_t)pcm_off * 5 / 4 + 1024;
-        if (e->d_energy.alloc(e->energy_capacity) || e->h_energy.alloc(e->energy_capacity)) return -1;
+        if (e->d_energy.alloc(e->energy_capacity)) return -1;
       }
       if ((size_t)blk_off > e->eblk_capacity) {
         e->d_eblk.release();
-        e->h_eblk.release();
         e->eblk_capacity = (size_t)blk_off * 5 / 4 + 64;
-        if (e->d_eblk.alloc(2 * e->eblk_capacity) || e->h_eblk.alloc(2 * e->eblk_capacity)) return -1;
+        if (e->d_eblk.alloc(2 * e->eblk_capacity)) return -1;
       }
       if (signal_energy(e->d_pcm.p, is_f32, e->d_utts.p, n, max_n, 32, e->d_energy.p, e->d_eblk.p,
                         e->d_eblk.p + e->eblk_capacity, st))
         return -1;
       e->times.n_launches++;
-      SW_CUDA_CHECK(cudaMemcpyAsync(e->h_energy.p, e->d_energy.p, (size_t)pcm_off * 4, cudaMemcpyDeviceToHost, st));
-      SW_CUDA_CHECK(cudaMemcpyAsync(e->h_eblk.p, e->d_eblk.p, 2 * e->eblk_capacity * 4, cudaMemcpyDeviceToHost, st));
-      e->times.d2h_bytes += (double)pcm_off * 4 + 2.0 * blk_off * 4;
+      // the energy stays in HBM: the token-time pass that reads it runs there too (refine_token_times)
       for (int i = 0; i < n; ++i) {
-        utts[i].energy = e->h_energy.p + mu[i].pcm_off;
-        utts[i].en_bmin = e->h_eblk.p + mu[i].blk_off;
-        utts[i].en_bmax = e->h_eblk.p + e->eblk_capacity + mu[i].blk_off;
+        utts[i].en_off = mu[i].pcm_off;
+        utts[i].blk_off = mu[i].blk_off;
         utts[i].n_energy = n_samples[i];
       }
     }
@@ -903,6 +848,86 @@ struct Run {
   std::vector<PickOut> first_store;
   std::vector<int> deferred_unref;
 
+  // ---- second half of the token-level timestamps for every segment the windows of a finished batch emitted:
+  // token times up, one kernel over the energy that never left the device, token times back (token_times.cu).
+  // Called from the post-processing thread of the batch, on the engine's post stream.
+  int refine_token_times(std::vector<Window>& ws) {
+    size_t n_seg = 0, n_tok = 0;
+    for (auto& w : ws)
+      for (int si : w.tt_segs) {
+        ++n_seg;
+        n_tok += utts[w.utt].res->segs[si].tokens.size();
+      }
+    if (n_seg == 0) return 0;
+    SW_CUDA_CHECK(cudaSetDevice(e->device));
+    if (n_seg > e->tt_seg_capacity) {
+      e->d_tt_seg.release();
+      e->h_tt_seg.release();
+      e->tt_seg_capacity = n_seg * 2 + 64;
+      if (e->d_tt_seg.alloc(e->tt_seg_capacity) || e->h_tt_seg.alloc(e->tt_seg_capacity)) return -1;
+    }
+    if (n_tok > e->tt_tok_capacity) {
+      e->d_tt_t.release();
+      e->h_tt_t.release();
+      e->d_tt_flag.release();
+      e->h_tt_flag.release();
+      e->d_tt_thold.release();
+      e->tt_tok_capacity = n_tok * 2 + 256;
+      if (e->d_tt_t.alloc(2 * e->tt_tok_capacity) || e->h_tt_t.alloc(2 * e->tt_tok_capacity) ||
+          e->d_tt_flag.alloc(e->tt_tok_capacity) || e->h_tt_flag.alloc(e->tt_tok_capacity) ||
+          e->d_tt_thold.alloc(e->tt_tok_capacity))
+        return -1;
+    }
+    const size_t cap = e->tt_tok_capacity;
+    long long *h0 = e->h_tt_t.p, *h1 = e->h_tt_t.p + cap;
+    size_t is = 0, it = 0;
+    for (auto& w : ws) {
+      const Utt& u = utts[w.utt];
+      for (int si : w.tt_segs) {
+        const sw_segment& sg = u.res->segs[si];
+        TtSeg& d = e->h_tt_seg.p[is++];
+        d.en_off = u.en_off;
+        d.blk_off = u.blk_off;
+        d.n_samples = u.n_energy;
+        d.tok_off = (int)it;
+        d.n_tok = (int)sg.tokens.size();
+        for (const sw_token_data& t : sg.tokens) {
+          h0[it] = t.t0;
+          h1[it] = t.t1;
+          e->h_tt_flag.p[it] = t.id < m.vocab.eot ? 1 : 0;
+          ++it;
+        }
+      }
+    }
+    cudaStream_t ps = e->post_stream;
+    SW_CUDA_CHECK(cudaMemcpyAsync(e->d_tt_seg.p, e->h_tt_seg.p, n_seg * sizeof(TtSeg), cudaMemcpyHostToDevice, ps));
+    SW_CUDA_CHECK(cudaMemcpyAsync(e->d_tt_t.p, h0, n_tok * sizeof(long long), cudaMemcpyHostToDevice, ps));
+    SW_CUDA_CHECK(cudaMemcpyAsync(e->d_tt_t.p + cap, h1, n_tok * sizeof(long long), cudaMemcpyHostToDevice, ps));
+    SW_CUDA_CHECK(cudaMemcpyAsync(e->d_tt_flag.p, e->h_tt_flag.p, n_tok, cudaMemcpyHostToDevice, ps));
+    if (token_time_refine(e->d_energy.p, e->d_eblk.p, e->d_eblk.p + e->eblk_capacity, e->d_tt_seg.p, (int)n_seg,
+                          e->d_tt_t.p, e->d_tt_t.p + cap, e->d_tt_flag.p, e->d_tt_thold.p, ps))
+      return -1;
+    SW_CUDA_CHECK(cudaMemcpyAsync(h0, e->d_tt_t.p, n_tok * sizeof(long long), cudaMemcpyDeviceToHost, ps));
+    SW_CUDA_CHECK(cudaMemcpyAsync(h1, e->d_tt_t.p + cap, n_tok * sizeof(long long), cudaMemcpyDeviceToHost, ps));
+    SW_CUDA_CHECK(cudaStreamSynchronize(ps));
+    it = 0;
+    for (auto& w : ws) {
+      Utt& u = utts[w.utt];
+      for (int si : w.tt_segs)
+        for (sw_token_data& t : u.res->segs[si].tokens) {
+          t.t0 = h0[it];
+          t.t1 = h1[it];
+          ++it;
+        }
+      w.tt_segs.clear();
+    }
+    tt_launches += 1;
+    tt_d2h_bytes += (double)n_tok * 2 * sizeof(long long);
+    return 0;
+  }
+  long tt_launches = 0;      // folded into the engine's counters by the main thread (collect)
+  double tt_d2h_bytes = 0;
+
   // ---- after the decode loop of one window: rank, fallback decision, segments, seek
   // returns true if the window must be re-run at the next temperature
   bool finish_window(Window& w) {
@@ -951,7 +976,7 @@ struct Run {
         sg.text = text;
         sg.speaker_turn_next = turn;
         sg.tokens.assign(tc.begin() + j0, tc.begin() + j1 + 1);
-        if (p.token_timestamps) token_timestamps(m, u, sg);
+        if (p.token_timestamps && token_timestamps(m, u, sg)) w.tt_segs.push_back((int)u.res->segs.size());
         u.res->segs.push_back(std::move(sg));
       };
       for (int i = 0; i < (int)tc.size(); ++i) {
@@ -1012,7 +1037,8 @@ struct Run {
     w.done = false;
   }
 
-  int run(const void* const* pcm, const int* n_samples, int n, bool is_f32, sw_result** out) {
+  int run(const void* const* pcm, const int* n_samples, int n, bool is_f32, sw_result** out,
+          const char* const* langs) {
     const Vocab& v = m.vocab;
     beam = p.strategy == 1 ? std::max(1, p.beam_size) : 1;
     best_of = std::max(1, p.best_of);
@@ -1045,11 +1071,12 @@ struct Run {
         u.lang = -1;
         continue;
       }
-      if (!p.language || !p.language[0] || strcmp(p.language, "auto") == 0) {
+      const char* lg = langs ? langs[i] : p.language;  // per utterance (sw_full_batch_*_lang) or the call's
+      if (!lg || !lg[0] || strcmp(lg, "auto") == 0) {
         need.push_back(i);
       } else {
-        u.lang = lang_id(p.language);
-        SW_CHECK(u.lang >= 0 && u.lang < v.n_langs, "unknown language '%s'", p.language);
+        u.lang = lang_id(lg);
+        SW_CHECK(u.lang >= 0 && u.lang < v.n_langs, "unknown language '%s'", lg);
       }
     }
     if (!need.empty() && detect_languages(need)) return -1;
@@ -1078,6 +1105,7 @@ struct Run {
       std::vector<Window> wins;
       std::vector<char> rerun;
       std::thread th;
+      std::string error;
       bool active = false, failed = false;
       ~Pending() {
         if (th.joinable()) th.join();
@@ -1106,6 +1134,10 @@ struct Run {
         for (int t = 1; t < nt; ++t) pool.emplace_back(work);
         work();
         for (auto& t : pool) t.join();
+        if (!pend.failed && refine_token_times(pend.wins)) {
+          pend.failed = true;
+          pend.error = last_error_string();  // thread-local: hand it to the thread that reports
+        }
       });
     };
     auto collect = [&]() -> int {
@@ -1114,7 +1146,11 @@ struct Run {
       pend.th.join();
       if (trace) fprintf(stderr, "[sw trace] waited %.1f ms for the host post-processing of %d windows\n", wall_ms() - tc0, (int)pend.wins.size());
       pend.active = false;
-      SW_CHECK(!pend.failed, "out of host memory while building results");
+      SW_CHECK(!pend.failed, "%s", pend.error.empty() ? "out of host memory while building results" : pend.error.c_str());
+      e->times.n_launches += tt_launches;
+      e->times.d2h_bytes += tt_d2h_bytes;
+      tt_launches = 0;
+      tt_d2h_bytes = 0;
       for (size_t i = 0; i < pend.wins.size(); ++i) {
         const Window& w = pend.wins[i];
         const Utt& u = utts[w.utt];
@@ -1171,13 +1207,13 @@ struct Run {
 }  // namespace
 
 int run_full_batch(Engine* e, const sw_full_params* params, const void* const* pcm, const int* n_samples,
-                   int n, bool is_f32, sw_result** out) {
+                   int n, bool is_f32, sw_result** out, const char* const* langs) {
   SW_CHECK(e && params && out && n > 0, "bad arguments");
   std::lock_guard<std::mutex> lk(e->mu);
   SW_CUDA_CHECK(cudaSetDevice(e->device));
   for (int i = 0; i < n; ++i) out[i] = nullptr;
   Run r(e, *params);
-  const int rc = r.run(pcm, n_samples, n, is_f32, out);
+  const int rc = r.run(pcm, n_samples, n, is_f32, out, langs);
   if (rc) {
     for (int i = 0; i < n; ++i) {
       delete out[i];
@@ -1188,13 +1224,14 @@ int run_full_batch(Engine* e, const sw_full_params* params, const void* const* p
 }
 
 int run_full_batch_lanes(sw_ctx* ctx, const sw_full_params* params, const void* const* pcm, const int* n_samples,
-                         int n, bool is_f32, sw_result** out) {
+                         int n, bool is_f32, sw_result** out, const char* const* langs) {
   SW_CHECK(ctx && ctx->e && params && out && n > 0, "bad arguments");
   const int n_lanes = 1 + (int)ctx->lanes.size();
-  if (n_lanes == 1 || n < 2) return run_full_batch(ctx->e, params, pcm, n_samples, n, is_f32, out);
+  if (n_lanes == 1 || n < 2) return run_full_batch(ctx->e, params, pcm, n_samples, n, is_f32, out, langs);
   // deal the utterances: lane k takes every n_lanes-th one, so ragged lengths spread evenly
   struct LaneJob {
     std::vector<const void*> pcm;
+    std::vector<const char*> langs;
     std::vector<int> n_samples, index;
     std::vector<sw_result*> out;
     int rc = 0;
@@ -1204,6 +1241,7 @@ int run_full_batch_lanes(sw_ctx* ctx, const sw_full_params* params, const void* 
   for (int i = 0; i < n; ++i) {
     LaneJob& j = jobs[i % n_lanes];
     j.pcm.push_back(pcm[i]);
+    if (langs) j.langs.push_back(langs[i]);
     j.n_samples.push_back(n_samples[i]);
     j.index.push_back(i);
   }
@@ -1213,7 +1251,8 @@ int run_full_batch_lanes(sw_ctx* ctx, const sw_full_params* params, const void* 
     j.out.assign(j.index.size(), nullptr);
     Engine* e = k == 0 ? ctx->e : ctx->lanes[k - 1];
     try {
-      j.rc = run_full_batch(e, params, j.pcm.data(), j.n_samples.data(), (int)j.index.size(), is_f32, j.out.data());
+      j.rc = run_full_batch(e, params, j.pcm.data(), j.n_samples.data(), (int)j.index.size(), is_f32, j.out.data(),
+                            langs ? j.langs.data() : nullptr);
     } catch (const std::exception& ex) {
       set_last_error("internal error: %s", ex.what());
       j.rc = -1;

@@ -32,12 +32,13 @@ struct sw_result {
 namespace sw {
 // pcm[i]: n_samples[i] host samples (int16 or f32). out[i] receives a new sw_result.
 // Returns 0, or non-zero on failure/abort (all out[i] are null then).
+// langs (optional): language of every utterance ("en", ..., "auto" / null = detect); null = params->language for all
 int run_full_batch(Engine* e, const sw_full_params* params, const void* const* pcm, const int* n_samples,
-                   int n, bool is_f32, sw_result** out);
+                   int n, bool is_f32, sw_result** out, const char* const* langs = nullptr);
 // The same over all lanes of a context: utterances are dealt to the lanes (they are independent units,
 // SURVEY.md §8e), one host thread per lane drives its engine, results land in the caller's order.
 int run_full_batch_lanes(sw_ctx* ctx, const sw_full_params* params, const void* const* pcm, const int* n_samples,
-                         int n, bool is_f32, sw_result** out);
+                         int n, bool is_f32, sw_result** out, const char* const* langs = nullptr);
 const char* last_error_string();
 void prosody_state_free(void* p);
 void resample_state_free(void* p);

@@ -32,8 +32,8 @@ struct SttEngine::Request {
     const sw_full_params &a = params, &b = o.params;
     return !abort_fn && !o.abort_fn && (pcm16 != nullptr) == (o.pcm16 != nullptr) && a.strategy == b.strategy &&
            a.beam_size == b.beam_size && a.best_of == b.best_of && a.temperature == b.temperature &&
-           a.translate == b.translate && a.tdrz_enable == b.tdrz_enable && language == o.language &&
-           prompt == o.prompt;
+           a.translate == b.translate && a.tdrz_enable == b.tdrz_enable && prompt == o.prompt;
+    // (the language may differ: it only selects a prompt token, sw_full_batch_*_lang takes one per utterance)
   }
 };
 
@@ -133,14 +133,16 @@ void SttEngine::dispatcher_loop() {
     std::vector<sw_result*> res(n, nullptr);
     for (int i = 0; i < n; ++i) lens[i] = batch[i]->n;
     int rc;
+    std::vector<const char*> langs(n);
+    for (int i = 0; i < n; ++i) langs[i] = batch[i]->language.c_str();
     if (batch[0]->pcm16) {
       std::vector<const int16_t*> ptrs(n);
       for (int i = 0; i < n; ++i) ptrs[i] = batch[i]->pcm16;
-      rc = sw_full_batch_pcm16(ctx_, &batch[0]->params, ptrs.data(), lens.data(), n, res.data());
+      rc = sw_full_batch_pcm16_lang(ctx_, &batch[0]->params, ptrs.data(), lens.data(), n, langs.data(), res.data());
     } else {
       std::vector<const float*> ptrs(n);
       for (int i = 0; i < n; ++i) ptrs[i] = batch[i]->pcm;
-      rc = sw_full_batch_f32(ctx_, &batch[0]->params, ptrs.data(), lens.data(), n, res.data());
+      rc = sw_full_batch_f32_lang(ctx_, &batch[0]->params, ptrs.data(), lens.data(), n, langs.data(), res.data());
     }
     const std::string err = rc ? sw_last_error() : "";
     ++batches_run_;

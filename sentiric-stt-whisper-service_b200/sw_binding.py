@@ -78,7 +78,7 @@ EXPORTS = [
     "sw_last_error", "sw_version", "sw_device_count", "sw_log_set", "sw_ctx_default_params",
     "sw_ctx_create", "sw_ctx_destroy", "sw_ctx_model_info", "sw_token_to_str", "sw_token_eot",
     "sw_lang_id", "sw_full_default_params", "sw_full", "sw_full_pcm16", "sw_full_batch_pcm16",
-    "sw_full_batch_f32", "sw_host_alloc", "sw_host_free", "sw_result_n_segments",
+    "sw_full_batch_f32", "sw_full_batch_pcm16_lang", "sw_full_batch_f32_lang", "sw_host_alloc", "sw_host_free", "sw_result_n_segments",
     "sw_result_segment_text", "sw_result_segment_t0", "sw_result_segment_t1",
     "sw_result_segment_speaker_turn_next", "sw_result_n_tokens", "sw_result_token_data",
     "sw_result_lang_id", "sw_result_n_decode_steps", "sw_result_n_windows", "sw_result_free",
@@ -118,6 +118,10 @@ def lib():
                                       C.POINTER(ci), ci, C.POINTER(vp)]
     L.sw_full_batch_f32.argtypes = [vp, C.POINTER(FullParams), C.POINTER(fp), C.POINTER(ci), ci,
                                     C.POINTER(vp)]
+    L.sw_full_batch_pcm16_lang.argtypes = [vp, C.POINTER(FullParams), C.POINTER(C.POINTER(C.c_int16)),
+                                           C.POINTER(ci), ci, C.POINTER(C.c_char_p), C.POINTER(vp)]
+    L.sw_full_batch_f32_lang.argtypes = [vp, C.POINTER(FullParams), C.POINTER(fp), C.POINTER(ci), ci,
+                                         C.POINTER(C.c_char_p), C.POINTER(vp)]
     L.sw_host_alloc.restype = vp
     L.sw_host_alloc.argtypes = [C.c_size_t]
     L.sw_host_free.argtypes = [vp]
@@ -207,13 +211,17 @@ class Engine:
         L.sw_result_free(r)
         return out
 
-    def full_batch_pcm16(self, pcms, params, collect=True):
+    def full_batch_pcm16(self, pcms, params, collect=True, languages=None):
         n = len(pcms)
         pcms = [np.ascontiguousarray(a, np.int16) for a in pcms]
         ptrs = (C.POINTER(C.c_int16) * n)(*[a.ctypes.data_as(C.POINTER(C.c_int16)) for a in pcms])
         lens = (C.c_int * n)(*[len(a) for a in pcms])
         res = (C.c_void_p * n)()
-        rc = self.L.sw_full_batch_pcm16(self.h, C.byref(params), ptrs, lens, n, res)
+        if languages is not None:
+            lg = (C.c_char_p * n)(*[None if x is None else x.encode() for x in languages])
+            rc = self.L.sw_full_batch_pcm16_lang(self.h, C.byref(params), ptrs, lens, n, lg, res)
+        else:
+            rc = self.L.sw_full_batch_pcm16(self.h, C.byref(params), ptrs, lens, n, res)
         if rc:
             raise RuntimeError("sw_full_batch_pcm16 rc=%d: %s" % (rc, last_error()))
         if not collect:
@@ -222,10 +230,13 @@ class Engine:
             return None
         return [self._collect(r) for r in res]
 
-    def full_batch_ptrs(self, ptrs, lens, n, params):
+    def full_batch_ptrs(self, ptrs, lens, n, params, languages=None):
         """bench path: ptrs/lens are prebuilt ctypes arrays (pinned host buffers); returns handles"""
         res = (C.c_void_p * n)()
-        rc = self.L.sw_full_batch_pcm16(self.h, C.byref(params), ptrs, lens, n, res)
+        if languages is not None:
+            rc = self.L.sw_full_batch_pcm16_lang(self.h, C.byref(params), ptrs, lens, n, languages, res)
+        else:
+            rc = self.L.sw_full_batch_pcm16(self.h, C.byref(params), ptrs, lens, n, res)
         if rc:
             raise RuntimeError("sw_full_batch_pcm16 rc=%d: %s" % (rc, last_error()))
         return res

@@ -663,3 +663,22 @@ def test_two_devices_in_one_process(swb, ora):
         compare_results(got, want)
     e0.close()
     e1.close()
+
+
+def test_language_per_utterance_in_one_batch(eng_tiny, ora_tiny):
+    """sw_full_batch_pcm16_lang: utterances in different languages (and one to detect) share a device pass and
+    get exactly what a single-language call gives each of them."""
+    clips = [synth_audio.utterance(8, i, seconds=6.0 + i) for i in range(6)]
+    langs = ["en", "tr", "de", "ja", None, "auto"]
+    mixed = eng_tiny.full_batch_pcm16(clips, eng_tiny.default_params(0, **GREEDY), languages=langs)
+    for c, lg, got in zip(clips, langs, mixed):
+        kw = dict(GREEDY, language=lg or "auto")
+        alone = eng_tiny.full_batch_pcm16([c], eng_tiny.default_params(0, **kw))[0]
+        compare_results(got, alone)
+        assert got["lang_id"] == alone["lang_id"]
+        if lg in ("tr", "ja"):
+            compare_results(got, ora_tiny.full(synth_audio.to_f32(c), ora_tiny.default_params(0, **kw)))
+    assert [m["lang_id"] for m in mixed[:4]] == [0, 9, 2, 7]
+    with pytest.raises(RuntimeError) as ei:
+        eng_tiny.full_batch_pcm16(clips[:2], eng_tiny.default_params(0, **GREEDY), languages=["en", "zz"])
+    assert "language" in str(ei.value)

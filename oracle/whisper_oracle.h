@@ -13,8 +13,17 @@
  * reference holds no golden vectors, tests or fixtures for this path
  * (SURVEY.md §0.3). This file restates the published algorithm of that
  * dependency anchored on the reference's own call sites
- * in src/stt_engine.cpp, and is cross-checked against the independent
- * HuggingFace Whisper implementation (tests/golden/make_golden.py).
+ * in src/stt_engine.cpp. It remains UNPINNED AGAINST UPSTREAM ITSELF; what pins
+ * it is the independent HuggingFace Whisper implementation:
+ *   - log-mel, encoder output, teacher-forced logits: tests/golden/make_golden.py
+ *     -> golden/micro_hf.npz (tests/test_oracle_golden.py);
+ *   - the logit rules (process_logits: suppression sets, timestamp grammar,
+ *     max_initial_ts, timestamp-mass rule) and greedy sequencing: HF's three
+ *     logits processors and generate(), tests/golden/make_rules_golden.py ->
+ *     golden/rules_hf.npz (tests/test_oracle_vs_hf_rules.py), with the two
+ *     intentional whisper.cpp-vs-OpenAI differences asserted by name.
+ * Recall-only (no independent counterpart here): seek / segment logic, beam
+ * search draws, sequence scoring, fallback thresholds, token-level timestamps.
  */
 #ifndef WHISPER_ORACLE_H
 #define WHISPER_ORACLE_H

@@ -64,3 +64,19 @@ def tiny_model():
 
 def seg_ids(result):
     return [t["id"] for s in result["segments"] for t in s["tokens"]]
+
+
+def diff(a, b, path=""):
+    """Where two nested results (dicts / lists / scalars) differ, as readable paths."""
+    out = []
+    if isinstance(a, dict):
+        for k in a:
+            out += diff(a[k], b[k], path + "/" + str(k))
+    elif isinstance(a, list):
+        if len(a) != len(b):
+            return [path + " len %d vs %d" % (len(a), len(b))]
+        for i, (x, y) in enumerate(zip(a, b)):
+            out += diff(x, y, path + "[%d]" % i)
+    elif a != b:
+        out.append("%s: %r vs %r" % (path, a, b))
+    return out

@@ -598,7 +598,7 @@ def test_decode_is_bit_deterministic_under_concurrent_load(swb, tiny_model):
     try:
         for _ in range(10):
             assert np.array_equal(a.decode_logits(tok), ref_logits)
-        from tools.dev_determinism import diff
+        from conftest import diff
         for _ in range(3):
             d = diff(ref_beam, a.full_batch_pcm16(clips[:6], a.default_params(1, **kw)))
             assert not d, d[:6]

@@ -32,6 +32,70 @@ const char* const k_non_speech[] = {
     "('", "(\"", "((", "))", "(((", ")))", "[[", "]]", "{{", "}}", "♪♪", "♪♪♪", "♩", "♪", "♫", "♬",
     "♭", "♮", "♯"};
 
+// ---- ggml tensor types this loader reads (ggml.h enum ggml_type): f32, f16 and the five "legacy" block
+// quantisations whisper.cpp's quantize tool writes (q4_0, q4_1, q5_0, q5_1, q8_0). Blocks of 32 values along
+// ne[0]; layouts restated from ggml's block_q* structs and dequantize_row_q* and checked against the independent
+// `gguf` Python package (tests/test_quantized_models.py). Quantised matrices are dequantised to f32 on the host
+// at load and then take the same f32 -> bf16 path as an f32 file: HBM always holds bf16.
+constexpr int QK = 32;
+inline bool type_supported(int t) { return t == 0 || t == 1 || t == 2 || t == 3 || t == 6 || t == 7 || t == 8; }
+inline bool type_quantised(int t) { return t >= 2; }
+inline size_t block_bytes(int t) {
+  switch (t) {
+    case 2: return 2 + 16;       // q4_0: f16 d, 16 bytes of nibbles
+    case 3: return 2 + 2 + 16;   // q4_1: f16 d, f16 m, nibbles
+    case 6: return 2 + 4 + 16;   // q5_0: f16 d, 32 high bits, nibbles
+    case 7: return 2 + 2 + 4 + 16;  // q5_1: f16 d, f16 m, high bits, nibbles
+    case 8: return 2 + 32;       // q8_0: f16 d, 32 int8
+    default: return 0;
+  }
+}
+inline size_t tensor_bytes(int t, int64_t nel) {
+  if (t == 0) return (size_t)nel * 4;
+  if (t == 1) return (size_t)nel * 2;
+  return (size_t)(nel / QK) * block_bytes(t);
+}
+inline float half_to_float(const uint8_t* p) {
+  _Float16 h;
+  memcpy(&h, p, 2);
+  return (float)h;
+}
+// n values (a multiple of 32) of type t at src -> f32
+void dequantise(int t, const uint8_t* src, float* dst, int64_t n) {
+  const size_t bb = block_bytes(t);
+  for (int64_t b = 0; b < n / QK; ++b, src += bb, dst += QK) {
+    const float d = half_to_float(src);
+    if (t == 8) {
+      const int8_t* q = reinterpret_cast<const int8_t*>(src + 2);
+      for (int j = 0; j < QK; ++j) dst[j] = q[j] * d;
+      continue;
+    }
+    const bool has_m = t == 3 || t == 7, has_h = t == 6 || t == 7;
+    const float m = has_m ? half_to_float(src + 2) : 0.f;
+    const uint8_t* p = src + 2 + (has_m ? 2 : 0);
+    uint32_t qh = 0;
+    if (has_h) {
+      memcpy(&qh, p, 4);
+      p += 4;
+    }
+    for (int j = 0; j < QK / 2; ++j) {
+      int x0 = p[j] & 0x0F, x1 = p[j] >> 4;
+      if (has_h) {
+        x0 |= ((qh >> (j + 0)) << 4) & 0x10;
+        x1 |= (qh >> (j + 12)) & 0x10;
+      }
+      if (has_m) {  // q4_1 / q5_1: unsigned code * d + m
+        dst[j] = x0 * d + m;
+        dst[j + QK / 2] = x1 * d + m;
+      } else {      // q4_0 / q5_0: signed around the middle code
+        const int off = has_h ? 16 : 8;
+        dst[j] = (x0 - off) * d;
+        dst[j + QK / 2] = (x1 - off) * d;
+      }
+    }
+  }
+}
+
 struct TInfo {
   int n_dims = 0, ttype = 0;
   int64_t ne[4] = {1, 1, 1, 1};
@@ -46,6 +110,7 @@ struct Loader {
   uint8_t* d_stage = nullptr;
   size_t stage_bytes = 0;
   cudaStream_t stream = nullptr;
+  std::vector<uint8_t> raw;  // a quantised tensor as stored
   ~Loader() {
     if (f) fclose(f);
     if (h_stage) cudaFreeHost(h_stage);
@@ -60,7 +125,7 @@ struct Loader {
     return &it->second;
   }
   int read_host(const TInfo& t, void* dst) {
-    const size_t bytes = (size_t)t.nel * (t.ttype == 1 ? 2 : 4);
+    const size_t bytes = tensor_bytes(t.ttype, t.nel);
     SW_CHECK(fseek(f, t.offset, SEEK_SET) == 0, "seek failed");
     SW_CHECK(fread(dst, 1, bytes, f) == bytes, "model file truncated");
     return 0;
@@ -71,9 +136,17 @@ struct Loader {
     if (!t) return -1;
     SW_CHECK(t->nel == expect, "tensor '%s' has %lld elements, expected %lld", name.c_str(),
              (long long)t->nel, (long long)expect);
-    const size_t bytes = (size_t)t->nel * (t->ttype == 1 ? 2 : 4);
-    SW_CHECK(bytes <= stage_bytes, "staging buffer too small for '%s'", name.c_str());
-    if (read_host(*t, h_stage)) return -1;
+    size_t bytes = tensor_bytes(t->ttype, t->nel);
+    SW_CHECK(bytes <= stage_bytes && (!type_quantised(t->ttype) || (size_t)t->nel * 4 <= stage_bytes),
+             "staging buffer too small for '%s'", name.c_str());
+    if (type_quantised(t->ttype)) {  // blocks -> f32 on the host, then the f32 path
+      raw.resize(bytes);
+      if (read_host(*t, raw.data())) return -1;
+      dequantise(t->ttype, raw.data(), reinterpret_cast<float*>(h_stage), t->nel);
+      bytes = (size_t)t->nel * 4;
+    } else if (read_host(*t, h_stage)) {
+      return -1;
+    }
     SW_CUDA_CHECK(cudaMemcpyAsync(d_stage, h_stage, bytes, cudaMemcpyHostToDevice, stream));
     if (t->ttype == 1) {
       if (convert_f16_to_bf16(reinterpret_cast<const uint16_t*>(d_stage), dst, t->nel, stream)) return -1;
@@ -91,6 +164,12 @@ struct Loader {
              (long long)t->nel, (long long)expect);
     out.resize(t->nel);
     if (t->ttype == 0) return read_host(*t, out.data());
+    if (type_quantised(t->ttype)) {
+      raw.resize(tensor_bytes(t->ttype, t->nel));
+      if (read_host(*t, raw.data())) return -1;
+      dequantise(t->ttype, raw.data(), out.data(), t->nel);
+      return 0;
+    }
     std::vector<uint16_t> tmp(t->nel);
     if (read_host(*t, tmp.data())) return -1;
     for (int64_t i = 0; i < t->nel; ++i) {
@@ -204,7 +283,13 @@ int load_impl(Model* m, const char* path) {
            hp.n_audio_ctx, hp.n_text_ctx);
   SW_CHECK(hp.n_mels == 80 || hp.n_mels == 128, "unsupported n_mels %d", hp.n_mels);
   SW_CHECK(hp.n_vocab >= 51864 && hp.n_vocab <= 52000, "unsupported n_vocab %d", hp.n_vocab);
-  SW_CHECK(hp.ftype == 0 || hp.ftype == 1, "quantised ggml files (ftype %d) are not supported", hp.ftype);
+  {
+    // ggml_ftype, possibly with the quantisation version in the thousands (GGML_QNT_VERSION_FACTOR): all f32 (0),
+    // mostly f16 (1), mostly q4_0 (2), q4_1 (3), q8_0 (7), q5_0 (8), q5_1 (9); k-quants (10+) are not read
+    const int ft = hp.ftype % 1000;
+    SW_CHECK(ft == 0 || ft == 1 || ft == 2 || ft == 3 || ft == 7 || ft == 8 || ft == 9,
+             "ggml ftype %d is not supported (f32, f16, q4_0, q4_1, q5_0, q5_1, q8_0 are)", hp.ftype);
+  }
   int32_t fm[2];
   SW_CHECK(fread(fm, 4, 2, L.f) == 2 && fm[0] == hp.n_mels && fm[1] == 201, "bad mel filterbank header");
   std::vector<float> filters((size_t)fm[0] * fm[1]);
@@ -220,7 +305,8 @@ int load_impl(Model* m, const char* path) {
     t.n_dims = hd[0];
     t.ttype = hd[2];
     SW_CHECK(t.n_dims >= 1 && t.n_dims <= 4 && hd[1] > 0 && hd[1] < 256, "corrupt tensor header");
-    SW_CHECK(t.ttype == 0 || t.ttype == 1, "quantised tensor type %d is not supported", t.ttype);
+    SW_CHECK(type_supported(t.ttype), "ggml tensor type %d is not supported (f32, f16, q4_0, q4_1, q5_0, q5_1, q8_0 are)",
+             t.ttype);
     t.nel = 1;
     for (int i = 0; i < t.n_dims; ++i) {
       int32_t v;
@@ -231,9 +317,12 @@ int load_impl(Model* m, const char* path) {
     std::string name(hd[1], '\0');
     SW_CHECK(fread(&name[0], 1, hd[1], L.f) == (size_t)hd[1], "corrupt tensor name");
     t.offset = ftell(L.f);
-    const size_t bytes = (size_t)t.nel * (t.ttype == 1 ? 2 : 4);
+    SW_CHECK(!type_quantised(t.ttype) || t.ne[0] % QK == 0, "quantised tensor '%s': row length %lld is not a multiple of 32",
+             name.c_str(), (long long)t.ne[0]);
+    const size_t bytes = tensor_bytes(t.ttype, t.nel);
     SW_CHECK(fseek(L.f, (long)bytes, SEEK_CUR) == 0, "seek failed");
     max_bytes = bytes > max_bytes ? bytes : max_bytes;
+    if (type_quantised(t.ttype)) max_bytes = std::max(max_bytes, (size_t)t.nel * 4);  // staged as f32
     L.idx[name] = t;
   }
   {
@@ -241,7 +330,7 @@ int load_impl(Model* m, const char* path) {
     fseek(L.f, 0, SEEK_END);
     const long fsz = ftell(L.f);
     for (auto& kv : L.idx) {
-      const size_t bytes = (size_t)kv.second.nel * (kv.second.ttype == 1 ? 2 : 4);
+      const size_t bytes = tensor_bytes(kv.second.ttype, kv.second.nel);
       SW_CHECK(kv.second.offset + (long)bytes <= fsz, "model file truncated in tensor '%s'", kv.first.c_str());
     }
   }

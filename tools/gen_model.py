@@ -272,9 +272,17 @@ def keyed_sure_prefix(info, n_samples, guard=3200):
     return kept
 
 
+QUANT_FTYPE = {"q4_0": 2, "q4_1": 3, "q8_0": 7, "q5_0": 8, "q5_1": 9}   # ggml_ftype (file header)
+QUANT_TTYPE = {"q4_0": 2, "q4_1": 3, "q5_0": 6, "q5_1": 7, "q8_0": 8}   # ggml_type (tensor header)
+
+
 class GgmlWriter:
-    def __init__(self, path):
+    def __init__(self, path, quant=None, twin=False):
+        """quant: one of QUANT_TTYPE - 2-D `.weight` matrices are stored block-quantised, as whisper.cpp's
+        quantize tool does (through the `gguf` package's reference quantisers). twin: store the DEQUANTISED
+        values as f32 instead - a file that must load to the very same bf16 weights as the quantised one."""
         self.f = open(path, "wb")
+        self.quant, self.twin = quant, twin
 
     def i32(self, *v):
         self.f.write(struct.pack("<%di" % len(v), *v))
@@ -284,11 +292,23 @@ class GgmlWriter:
         dims = list(arr.shape)
         nb = name.encode()
         ttype = 1 if f16 else 0
+        data = None
+        if self.quant and len(dims) == 2 and name.endswith(".weight") and dims[1] % 32 == 0 and f16:
+            from gguf import GGMLQuantizationType, quants
+            qt = GGMLQuantizationType(QUANT_TTYPE[self.quant])
+            q = quants.quantize(arr.astype(np.float32), qt)
+            if self.twin:
+                ttype, data = 0, quants.dequantize(q, qt).astype(np.float32)
+            else:
+                ttype, data = QUANT_TTYPE[self.quant], q
         self.i32(len(dims), len(nb), ttype)
         for d in reversed(dims):  # ggml order: ne[0] is the contiguous dim
             self.i32(d)
         self.f.write(nb)
-        (arr.astype(np.float16) if f16 else arr.astype(np.float32)).tofile(self.f)
+        if data is not None:
+            np.ascontiguousarray(data).tofile(self.f)
+        else:
+            (arr.astype(np.float16) if f16 else arr.astype(np.float32)).tofile(self.f)
 
     def close(self):
         self.f.close()
@@ -297,15 +317,17 @@ class GgmlWriter:
 def generate(path, size, seed=None, script_len=0, script_rms=0.5, qk_gain=4.0, ln_f_gain=None,
              script_end_cs=3000, w_std=0.02, emb_std=0.02, f32_all=False, verbose=False,
              script_final_pair=False, script_first_ts=0, keyed=0, keyed_beta=1.2, keyed_delta=0.6, keyed_attn=1.5,
-             keyed_gain=0.7):
+             keyed_gain=0.7, quant=None, quant_twin=False):
     d, n_head, n_layer, n_mel, n_vocab = SIZES[size]
     if seed is None:
         seed = int.from_bytes(hashlib.sha256(size.encode()).digest()[:4], "little")
     rng = np.random.default_rng(seed)
     sp = special_tokens(n_vocab)
-    wr = GgmlWriter(path)
+    wr = GgmlWriter(path, quant=quant, twin=quant_twin)
     wr.f.write(struct.pack("<I", 0x67676D6C))
     ftype = 0 if f32_all else 1
+    if quant and not quant_twin:
+        ftype = 2000 + QUANT_FTYPE[quant]  # quantisation version 2 in the thousands, as ggml writes it
     wr.i32(n_vocab, N_AUDIO_CTX, d, n_head, n_layer, N_TEXT_CTX, d, n_head, n_layer, n_mel, ftype)
     fb = mel_filterbank(n_mel)
     wr.i32(n_mel, 201)

@@ -33,6 +33,11 @@ def read_ggml(path):
                 a = np.frombuffer(f.read(4 * n), np.float32).reshape(shape).copy()
             elif ttype == 1:
                 a = np.frombuffer(f.read(2 * n), np.float16).reshape(shape).astype(np.float32)
+            elif ttype in (2, 3, 6, 7, 8):  # q4_0, q4_1, q5_0, q5_1, q8_0: dequantised by the gguf package
+                from gguf import GGMLQuantizationType, quants
+                bb = {2: 18, 3: 20, 6: 22, 7: 24, 8: 34}[ttype]
+                raw = np.frombuffer(f.read(n // 32 * bb), np.uint8).reshape(shape[:-1] + (shape[-1] // 32 * bb,))
+                a = quants.dequantize(raw, GGMLQuantizationType(ttype)).astype(np.float32)
             else:
                 raise ValueError("unsupported ggml tensor type %d" % ttype)
             tensors[name] = a

@@ -92,3 +92,36 @@ def test_keyed_wrong_audio_changes_gpu_tokens(swb):
     got = e.full_batch_pcm16([good, slow, np.zeros(16000 * 30, np.int16)], e.default_params(0, **GREEDY))
     assert seg_ids(got[0]) == want and seg_ids(got[1]) != want and seg_ids(got[2]) != want
     e.close()
+
+
+@pytest.mark.gpu
+def test_keyed_long_form_follows_the_audio_window_by_window(swb, ora):
+    """A 101 s utterance = three different 30 s keyed clips + 11 s of a fourth: four windows whose `seek` advances
+    by the last timestamp of the previous one. Every window must spell the symbols of ITS 30 s of audio (a window
+    cut at the wrong frame, or a stale cross-KV, would spell something else), in a batch next to short utterances
+    that finish early. T = 0.5 / best_of 1: above 0.5 whisper.cpp does not condition a window on the previous
+    text, so the scripted positions hold in every window; the sharpened distribution puts > 0.99 on one token."""
+    from test_gpu_parity import compare_results
+    path, info = model_file("tiny", script_len=40, keyed=4)
+    k = info["keyed"]
+    seeds = (400, 401, 402)
+    syms = [synth_audio.keyed_symbols(k, s) for s in seeds]
+    tail = synth_audio.keyed_clip(k, syms[0], seed=403)[: 16000 * 11]
+    long_clip = np.concatenate([synth_audio.keyed_clip(k, sy, seed=s) for sy, s in zip(syms, seeds)] + [tail])
+    short = synth_audio.keyed_clip(k, syms[1], seed=401)[: 16000 * 9]
+    kw = dict(language="en", temperature=0.5, temperature_inc=0.0, best_of=1, suppress_nst=1, token_timestamps=1)
+    e = swb.Engine(path, max_batch=4)
+    got = e.full_batch_pcm16([short, long_clip, short[: 16000 * 3], long_clip[: 16000 * 61]], e.default_params(0, **kw))
+    want_ids = sum([gen_model.keyed_expected_tokens(info, sy) for sy in syms], [])
+    ids = seg_ids(got[1])
+    assert got[1]["n_windows"] == 4 and ids[: len(want_ids)] == want_ids
+    ks = gen_model.keyed_sure_prefix(info, len(tail))
+    assert ids[len(want_ids): len(want_ids) + ks] == gen_model.keyed_expected_tokens(info, syms[0])[:ks]
+    assert [s["t0"] for s in got[1]["segments"]][::2] == [0, 3000, 6000, 9000]
+    two = seg_ids(got[3])
+    assert two[: 2 * len(want_ids) // 3] == want_ids[: 2 * len(want_ids) // 3]
+    o = ora.Oracle(path, weight_round=False, act_round=ora.ACT_F16)
+    compare_results(got[1], o.full(synth_audio.to_f32(long_clip), o.default_params(0, **kw)), p_tol=2e-2,
+                    check_windows=False)
+    compare_results(got[0], o.full(synth_audio.to_f32(short), o.default_params(0, **kw)), p_tol=2e-2, check_windows=False)
+    e.close()

@@ -199,9 +199,10 @@ def main():
                     help="N > 0: ONE process, N contexts on devices 0..N-1 driven by N host threads (the in-process "
                          "dispatcher of SURVEY.md §8(e)) instead of one process per GPU; prints the same line with "
                          "mode=inproc")
-    ap.add_argument("--facade", action="store_true",
-                    help="also measure the reference-facing class: caller threads on SttEngine::transcribe_pcm16 with "
-                         "pageable vectors (host/stt_cli bench mode) -> e2e_facade")
+    ap.add_argument("--facade", action="store_true", default=True,
+                    help="(default) also measure the reference-facing class: caller threads on SttEngine::transcribe_pcm16 "
+                         "with pageable vectors (host/stt_cli bench mode) -> e2e_facade")
+    ap.add_argument("--no-facade", dest="facade", action="store_false")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.model:

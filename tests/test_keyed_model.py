@@ -123,5 +123,8 @@ def test_keyed_long_form_follows_the_audio_window_by_window(swb, ora):
     o = ora.Oracle(path, weight_round=False, act_round=ora.ACT_F16)
     compare_results(got[1], o.full(synth_audio.to_f32(long_clip), o.default_params(0, **kw)), p_tol=2e-2,
                     check_windows=False)
-    compare_results(got[0], o.full(synth_audio.to_f32(short), o.default_params(0, **kw)), p_tol=2e-2, check_windows=False)
+    # the 9 s neighbour: the tokens its audio decides (past its end the alternatives tie and T = 0.5 draws decide)
+    ks = gen_model.keyed_sure_prefix(info, len(short))
+    want_short = o.full(synth_audio.to_f32(short), o.default_params(0, **kw))
+    assert ks >= 8 and seg_ids(got[0])[:ks] == seg_ids(want_short)[:ks] == gen_model.keyed_expected_tokens(info, syms[1])[:ks]
     e.close()

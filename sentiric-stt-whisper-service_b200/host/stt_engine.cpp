@@ -73,6 +73,10 @@ SttEngine::SttEngine(const Settings& settings) : settings_(settings) {
             "SttEngine::set_vad_fn() installs one; silence is decoded by Whisper and filtered by no_speech_thold.\n",
             vad_path.c_str(), f ? "is present but cannot be evaluated" : "is missing");
   }
+  {
+    sw_stats st;
+    if (sw_ctx_get_stats(ctx_, &st, 0) == 0 && st.n_lanes > 1) lanes_ = (int)st.n_lanes;
+  }
   dispatcher_ = std::thread([this] { dispatcher_loop(); });
 }
 
@@ -111,10 +115,12 @@ void SttEngine::dispatcher_loop() {
       std::unique_lock<std::mutex> lk(q_mutex_);
       q_cv_.wait(lk, [this] { return stopping_ || !queue_.empty(); });
       if (stopping_ && queue_.empty()) return;
-      if (settings_.batch_window_us > 0 && (int)queue_.size() < settings_.max_batch) {
+      // a full device pass is max_batch windows on EVERY lane of the context (two lanes: 2 x max_batch)
+      const int full_pass = settings_.max_batch * lanes_;
+      if (settings_.batch_window_us > 0 && (int)queue_.size() < full_pass) {
         // give concurrent callers a moment to join this device pass
         q_cv_.wait_for(lk, std::chrono::microseconds(settings_.batch_window_us),
-                       [this] { return stopping_ || (int)queue_.size() >= settings_.max_batch; });
+                       [this, full_pass] { return stopping_ || (int)queue_.size() >= full_pass; });
       }
       Request* head = queue_.front();
       queue_.pop_front();

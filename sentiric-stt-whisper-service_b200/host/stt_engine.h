@@ -122,4 +122,5 @@ class SttEngine {
   bool stopping_ = false;
   std::thread dispatcher_;
   long batches_run_ = 0, requests_batched_ = 0;
+  int lanes_ = 1;  // lanes of the context: a full device pass is max_batch * lanes_ requests
 };

@@ -121,13 +121,17 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
                     const int* d_grp_start, const int* d_grp_count, int n_groups, int max_count, int R,
                     int T, int d, int n_head, float* ws, bf16* out, cudaStream_t stream,
                     cudaEvent_t ev_main_done = nullptr, unsigned ev_flags = 0,  // event after the main kernel
-                    int max_ctas = 0);  // cap on the persistent grid (0 = one CTA per SM)
+                    int max_ctas = 0,   // cap on the persistent grid (0 = one CTA per SM)
+                    int row0 = 0,       // the groups cover rows [row0, row0 + R) of q / ws / out (grp_start is absolute)
+                    cudaEvent_t ev_dep = nullptr);  // plain record after the main kernel (a dependency edge for another stream)
 
 // weight-streaming GEMM for <= 64-row blocks (skinny_gemm.cu): out = X . W^T
 //   split == 1: out bf16 [R][ldo] = act(acc + bias);   split > 1: partial f32 [split][R][N] (raw sums)
 int skinny_split_for(int N, int K);
+// stages: depth of the shared-memory ring (0 = default 8; 4 = 53 KB per CTA, small enough to share an SM with a
+// resident cross-attention CTA)
 int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, const float* bias, int gelu,
-                bf16* out, int ldo, float* partial, int split, cudaStream_t stream);
+                bf16* out, int ldo, float* partial, int split, cudaStream_t stream, int stages = 0);
 
 // ------------------------------------------------------------------ prosody (prosody.cu)
 // per-segment DSP of prosody_extractor.cpp:31-224 for all segments of an utterance

@@ -219,7 +219,7 @@ int skinny_split_for(int N, int K) {
 }
 
 int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, const float* bias, int gelu,
-                bf16* out, int ldo, float* partial, int split, cudaStream_t stream) {
+                bf16* out, int ldo, float* partial, int split, cudaStream_t stream, int stages) {
   if (R <= 0) return 0;
   SW_CHECK(K % SK_BK == 0 && ldx % 8 == 0 && N % 2 == 0, "skinny_gemm: unsupported shape N=%d K=%d ldx=%d", N, K, ldx);
   SW_CHECK(split >= 1 && split <= 32 && (split == 1 || partial), "skinny_gemm: split-K needs a partial buffer");
@@ -230,11 +230,12 @@ int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, cons
   // ring depth: 8 stages (two CTAs of ~100 KB per SM) when the launch has the GPU to itself; SW_SKINNY_STAGES
   // selects a shallower ring (development: 4 stages = 53 KB, small enough to share an SM with a resident
   // cross-attention CTA of the other lane)
-  static const int n_stages = [] {
+  static const int env_stages = [] {
     const char* v = getenv("SW_SKINNY_STAGES");
-    const int n = v ? atoi(v) : SK_STAGES;
-    return n >= 2 && n <= SK_STAGES ? n : SK_STAGES;
+    const int n = v ? atoi(v) : 0;
+    return n >= 2 && n <= SK_STAGES ? n : 0;
   }();
+  const int n_stages = env_stages ? env_stages : (stages >= 2 && stages <= SK_STAGES ? stages : SK_STAGES);
   static SmemOptIn opt_in32, opt_in40;  // per device (host_common.h)
   SW_CUDA_CHECK(opt_in32.ensure(skinny_gemm_kernel<32>, SkCfg<32>::smem(SK_STAGES)));
   SW_CUDA_CHECK(opt_in40.ensure(skinny_gemm_kernel<40>, SkCfg<40>::smem(SK_STAGES)));

@@ -310,7 +310,7 @@ size_t cross_attention_ws_floats(int R, int d, int n_head) {
 int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d_grp_win,
                     const int* d_grp_start, const int* d_grp_count, int n_groups, int max_count, int R,
                     int T, int d, int n_head, float* ws, bf16* out, cudaStream_t stream,
-                    cudaEvent_t ev_main_done, unsigned ev_flags, int max_ctas) {
+                    cudaEvent_t ev_main_done, unsigned ev_flags, int max_ctas, int row0, cudaEvent_t ev_dep) {
   if (n_groups <= 0 || R <= 0) return 0;
   SW_CHECK(d == n_head * 64, "cross_attention: head dim must be 64");
   SW_CHECK(max_count >= 1 && max_count <= 8, "cross_attention: group of %d rows", max_count);
@@ -349,8 +349,10 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
   }
 #undef XA_LAUNCH
   if (ev_main_done) SW_CUDA_CHECK(cudaEventRecordWithFlags(ev_main_done, stream, ev_flags));
-  SW_CUDA_CHECK(launch_pdl(cross_combine_kernel, dim3(R, (n_head + 3) / 4), dim3(32), 0, stream, ws, n_chunks, d,
-                           n_head, out));
+  if (ev_dep) SW_CUDA_CHECK(cudaEventRecord(ev_dep, stream));
+  // the main kernel addresses rows through grp_start (absolute); the merge walks this call's rows row0 .. row0 + R
+  SW_CUDA_CHECK(launch_pdl(cross_combine_kernel, dim3(R, (n_head + 3) / 4), dim3(32), 0, stream,
+                           ws + (int64_t)row0 * n_chunks * (d + 2 * n_head), n_chunks, d, n_head, out + (int64_t)row0 * d));
   return 0;
 }
 

@@ -333,13 +333,16 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
   const int box[3] = {64, XA_KEYS, 2 * n_head};
   if (make_tma_map_3d_bf16(&map, kv, dims, strides, box)) return -1;
   const int threads = (n_cons + 1) * 32;
+  // `ws` holds the partials of THIS call's rows (row0 .. row0 + R) from its start; the main kernel addresses rows
+  // absolutely (through grp_start), so it gets the pointer moved back by row0 rows of n_chunks partials
+  float* ws_main = ws - (int64_t)row0 * n_chunks * (d + 2 * n_head);
 #define XA_LAUNCH(H)                                                                                  \
   do {                                                                                                \
     static SmemOptIn opt_in; /* per device (host_common.h) */                                         \
     SW_CUDA_CHECK(opt_in.ensure(cross_attention_kernel<H>, (int)smem));                               \
     SW_CUDA_CHECK(launch_pdl(cross_attention_kernel<H>, dim3(grid), dim3(threads), smem, stream, map, \
                              q, d_grp_win, d_grp_start, d_grp_count, T, d, n_head, n_cons, spc,        \
-                             n_stages, n_chunks, n_items, ws, 0u));                                    \
+                             n_stages, n_chunks, n_items, ws_main, 0u));                               \
   } while (0)
   switch (hpw) {
     case 1: XA_LAUNCH(1); break;
@@ -351,8 +354,8 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
   if (ev_main_done) SW_CUDA_CHECK(cudaEventRecordWithFlags(ev_main_done, stream, ev_flags));
   if (ev_dep) SW_CUDA_CHECK(cudaEventRecord(ev_dep, stream));
   // the main kernel addresses rows through grp_start (absolute); the merge walks this call's rows row0 .. row0 + R
-  SW_CUDA_CHECK(launch_pdl(cross_combine_kernel, dim3(R, (n_head + 3) / 4), dim3(32), 0, stream,
-                           ws + (int64_t)row0 * n_chunks * (d + 2 * n_head), n_chunks, d, n_head, out + (int64_t)row0 * d));
+  SW_CUDA_CHECK(launch_pdl(cross_combine_kernel, dim3(R, (n_head + 3) / 4), dim3(32), 0, stream, ws, n_chunks, d, n_head,
+                           out + (int64_t)row0 * d));
   return 0;
 }
 

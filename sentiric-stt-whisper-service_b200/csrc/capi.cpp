@@ -53,8 +53,7 @@ sw_ctx* sw_ctx_create(const char* path, const sw_ctx_params* params) {
   }
   Engine* e = sw::engine_create(path, &pi);
   if (!e) return nullptr;
-  if (interleave)
-    if (const char* v = getenv("SW_XA_CTAS")) e->xa_max_ctas = atoi(v);
+  if (const char* v = getenv("SW_XA_CTAS")) e->xa_max_ctas = atoi(v);  // development: cap also without lanes
   sw_ctx* c = new sw_ctx();
   c->e = e;
   params = &pi;

@@ -43,11 +43,15 @@ __global__ void __launch_bounds__((XA_MAX_CONSUMERS + 1) * 32, 1)
 cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* __restrict__ q,
                        const int* __restrict__ grp_win, const int* __restrict__ grp_start,
                        const int* __restrict__ grp_count, int T, int d, int n_head, int n_cons, int spc,
-                       int n_stages, int n_chunks, int n_items, float* __restrict__ ws, uint32_t zero) {
+                       int n_stages, int n_chunks, int n_items, float* __restrict__ ws, uint32_t zero, int n_hsplit) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t sbase = smem_u32(smem);
-  const int stage_bytes = XA_KEYS * 2 * d * 2;
+  // a work item is (window, chunk of keys, group of heads): with n_hsplit = 2 a CTA streams the K and V rows of half
+  // the heads only, so a stage is half as large and the ring twice as deep (large-v3: 5 x 40 KB instead of 2 x 80 KB)
+  const int nh_cta = n_head / n_hsplit;  // heads of one item
+  const int half_bytes = XA_KEYS * nh_cta * 64 * 2;  // the K tiles (or the V tiles) of a stage
+  const int stage_bytes = 2 * half_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * stage_bytes);
   uint64_t* empty = full + n_stages;
 
@@ -71,7 +75,8 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
     if (elect_one_sync()) {  // not a lane test: one UTMALDG per load instead of a loop over the active lanes
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int g = item / n_chunks, chunk = item - g * n_chunks;
+        const int gc = item / n_hsplit, hh = item - gc * n_hsplit;
+        const int g = gc / n_chunks, chunk = gc - g * n_chunks;
         const int win = grp_win[g];
         const int key_begin = chunk * spc * XA_KEYS;
         const int key_end = min(T, key_begin + spc * XA_KEYS);
@@ -81,7 +86,11 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
           const uint32_t ph = (it / n_stages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], stage_bytes);
-          tma_load_3d(smem + (size_t)s * stage_bytes, &map_kv, &full[s], 0, win * T + key_begin + i * XA_KEYS, 0);
+          uint8_t* dst = smem + (size_t)s * stage_bytes;
+          const int key = win * T + key_begin + i * XA_KEYS;
+          // segments of the [K row | V row] cache line: K heads 0 .. n_head-1, then V heads
+          tma_load_3d(dst, &map_kv, &full[s], 0, key, hh * nh_cta);
+          tma_load_3d(dst + half_bytes, &map_kv, &full[s], 0, key, n_head + hh * nh_cta);
         }
       }
     }
@@ -96,12 +105,14 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
   // raw query fragments of the next item: [head slot][k-step][a0, a2]
   uint32_t qn[HPW][4][2];
   auto prefetch_q = [&](int item) {
-    const int g = item / n_chunks;
+    const int gc = item / n_hsplit, hh = item - gc * n_hsplit;
+    const int g = gc / n_chunks;
     const int cnt = grp_count[g], r0 = grp_start[g];
 #pragma unroll
     for (int hs = 0; hs < HPW; ++hs) {
-      const int h = warp + hs * n_cons;
-      const bool ok = h < n_head && g8 < cnt;
+      const int hl = warp + hs * n_cons;          // head within the item
+      const int h = hh * nh_cta + hl;
+      const bool ok = hl < nh_cta && g8 < cnt;
       const bf16* qp = q + (int64_t)(r0 + g8) * d + h * 64 + 2 * t4;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
@@ -113,7 +124,8 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
   if ((int)blockIdx.x < n_items) prefetch_q(blockIdx.x);
   int it = 0;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int g = item / n_chunks, chunk = item - g * n_chunks;
+    const int gc = item / n_hsplit, hh = item - gc * n_hsplit;
+    const int g = gc / n_chunks, chunk = gc - g * n_chunks;
     const int r0 = grp_start[g], cnt = grp_count[g];
     const int key_begin = chunk * spc * XA_KEYS;
     const int key_end = min(T, key_begin + spc * XA_KEYS);
@@ -145,9 +157,9 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
       uint32_t dep = 0;  // one result register of every ldmatrix of this stage (mbar_arrive_after_reads)
 #pragma unroll
       for (int hs = 0; hs < HPW; ++hs) {
-        const int h = warp + hs * n_cons;
-        if (h >= n_head) continue;
-        const uint32_t kt = st + h * 2048, vt = st + (n_head + h) * 2048;  // [16 keys][128 B] swizzled tiles
+        const int hl = warp + hs * n_cons;
+        if (hl >= nh_cta) continue;
+        const uint32_t kt = st + hl * 2048, vt = st + half_bytes + hl * 2048;  // [16 keys][128 B] swizzled tiles
         float sc[2][4];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
@@ -213,8 +225,9 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
     // ---- partial result of this (window, chunk): unnormalised O, running max m and sum l per head
 #pragma unroll
     for (int hs = 0; hs < HPW; ++hs) {
-      const int h = warp + hs * n_cons;
-      if (h >= n_head) continue;
+      const int hl = warp + hs * n_cons;
+      if (hl >= nh_cta) continue;
+      const int h = hh * nh_cta + hl;
       float ls = l[hs];
       ls += __shfl_xor_sync(0xffffffffu, ls, 1);
       ls += __shfl_xor_sync(0xffffffffu, ls, 2);
@@ -272,7 +285,8 @@ cross_combine_kernel(const float* __restrict__ ws, int n_chunks, int d, int n_he
 int xa_num_sms() { return device_sm_count(); }  // of the current device, cached per ordinal (host_common.h)
 
 // stages per work item: the value that leaves the fewest idle SM-slots in the last wave
-void xa_plan(int n_groups, int T, int d, int max_ctas, int* spc_out, int* n_chunks, int* n_stages, int* grid) {
+void xa_plan(int n_groups, int T, int d, int max_ctas, int n_hsplit, int* spc_out, int* n_chunks, int* n_stages,
+             int* grid) {
   const int total_stages = (T + XA_KEYS - 1) / XA_KEYS;
   int sms = xa_num_sms();
   if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
@@ -281,10 +295,10 @@ void xa_plan(int n_groups, int T, int d, int max_ctas, int* spc_out, int* n_chun
   for (int spc = 3; spc <= 16; ++spc) {
     const int nch = (total_stages + spc - 1) / spc;
     if (nch > XA_MAX_CHUNKS) continue;
-    const int items = n_groups * nch;
+    const int items = n_groups * nch * n_hsplit;
     const int g = items < sms ? items : sms;
     const int rounds = (items + g - 1) / g;
-    const double eff = (double)n_groups * total_stages / ((double)g * rounds * spc) * (g / (double)sms);
+    const double eff = (double)n_groups * n_hsplit * total_stages / ((double)g * rounds * spc) * (g / (double)sms);
     if (eff >= best_eff) {
       best_eff = eff;
       best_spc = spc;
@@ -292,9 +306,9 @@ void xa_plan(int n_groups, int T, int d, int max_ctas, int* spc_out, int* n_chun
   }
   *spc_out = best_spc;
   *n_chunks = (total_stages + best_spc - 1) / best_spc;
-  const int items = n_groups * *n_chunks;
+  const int items = n_groups * *n_chunks * n_hsplit;
   *grid = items < sms ? items : sms;
-  const int stage_bytes = XA_KEYS * 2 * d * 2;
+  const int stage_bytes = XA_KEYS * 2 * (d / n_hsplit) * 2;
   int ns = (220 * 1024) / stage_bytes;
   if (ns > 8) ns = 8;
   if (ns < 2) ns = 2;
@@ -314,23 +328,31 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
   if (n_groups <= 0 || R <= 0) return 0;
   SW_CHECK(d == n_head * 64, "cross_attention: head dim must be 64");
   SW_CHECK(max_count >= 1 && max_count <= 8, "cross_attention: group of %d rows", max_count);
-  // consumer warps: the largest divisor of n_head that is <= 10, so every warp owns the same number of heads
+  // wide models: a CTA takes half the heads of a (window, chunk), so a stage is 40 KB instead of 80 KB (large-v3) and
+  // the ring 5 deep instead of 2 - with two stages an SM streamed 55 GB/s whatever the grid (64, 96 CTAs measured),
+  // i.e. the ring, not HBM, bounded every capped launch. SW_XA_HSPLIT=1 restores whole windows per CTA (development).
+  static const int force_hsplit = getenv("SW_XA_HSPLIT") ? atoi(getenv("SW_XA_HSPLIT")) : 0;
+  int n_hsplit = (XA_KEYS * 2 * d * 2 * 3 > 220 * 1024 && n_head % 2 == 0) ? 2 : 1;
+  if (force_hsplit == 1 || (force_hsplit == 2 && n_head % 2 == 0)) n_hsplit = force_hsplit;
+  const int nh_cta = n_head / n_hsplit;
+  // consumer warps: the largest divisor of the item's heads that is <= 10, so every warp owns the same number of heads
   int n_cons = 1;
   for (int c = 1; c <= XA_MAX_CONSUMERS; ++c)
-    if (n_head % c == 0) n_cons = c;
-  const int hpw = n_head / n_cons;
+    if (nh_cta % c == 0) n_cons = c;
+  const int hpw = nh_cta / n_cons;
   SW_CHECK(hpw <= XA_MAX_HPW, "cross_attention: %d heads per warp", hpw);
   int spc, n_chunks, n_stages, grid;
-  xa_plan(n_groups, T, d, max_ctas, &spc, &n_chunks, &n_stages, &grid);
-  const int stage_bytes = XA_KEYS * 2 * d * 2;
+  xa_plan(n_groups, T, d, max_ctas, n_hsplit, &spc, &n_chunks, &n_stages, &grid);
+  const int stage_bytes = XA_KEYS * 2 * (d / n_hsplit) * 2;
   const size_t smem = (size_t)n_stages * stage_bytes + 1024 + 2 * n_stages * sizeof(uint64_t);
   SW_CHECK(smem <= 227 * 1024, "cross_attention: %zu bytes of shared memory", smem);
-  const int n_items = n_groups * n_chunks;
-  // the cache as a 3-D tensor {64 dims, keys, 2*n_head segments of the [K | V] row}
+  const int n_items = n_groups * n_chunks * n_hsplit;
+  // the cache as a 3-D tensor {64 dims, keys, 2*n_head segments of the [K | V] row}; one box = the K (or V) tiles
+  // of an item's heads
   CUtensorMap map;
   const int64_t dims[3] = {64, kv_rows, 2 * n_head};
   const int64_t strides[2] = {(int64_t)2 * d * 2, 128};
-  const int box[3] = {64, XA_KEYS, 2 * n_head};
+  const int box[3] = {64, XA_KEYS, nh_cta};
   if (make_tma_map_3d_bf16(&map, kv, dims, strides, box)) return -1;
   const int threads = (n_cons + 1) * 32;
   // `ws` holds the partials of THIS call's rows (row0 .. row0 + R) from its start; the main kernel addresses rows
@@ -342,7 +364,7 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
     SW_CUDA_CHECK(opt_in.ensure(cross_attention_kernel<H>, (int)smem));                               \
     SW_CUDA_CHECK(launch_pdl(cross_attention_kernel<H>, dim3(grid), dim3(threads), smem, stream, map, \
                              q, d_grp_win, d_grp_start, d_grp_count, T, d, n_head, n_cons, spc,        \
-                             n_stages, n_chunks, n_items, ws_main, 0u));                               \
+                             n_stages, n_chunks, n_items, ws_main, 0u, n_hsplit));                     \
   } while (0)
   switch (hpw) {
     case 1: XA_LAUNCH(1); break;

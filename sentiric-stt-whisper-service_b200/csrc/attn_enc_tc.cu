@@ -35,6 +35,10 @@ constexpr int ATT_THREADS = 320;       // warp 0: TMA, warp 1: TMEM + MMA issue,
 // over the scores it came from and double-buffered O instead: P V(j) then had to be issued BEFORE S(j+1) and sat
 // on the serial chain; 1.44 vs 1.37 ms per layer for 64 windows.)
 constexpr int TMEM_COLS = 256, TM_P = 128, TM_O = 192;
+#ifndef SW_ATT_POLY
+#define SW_ATT_POLY 1
+#endif
+constexpr bool ATT_POLY = SW_ATT_POLY != 0;
 
 // MN-major 128B-swizzled operand (the V tile: rows = keys (K), 64 dims (MN) contiguous per row):
 // canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> SBO = 1024 B between 8-key groups
@@ -52,6 +56,21 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// 2^x for x <= 0 on the FMA / ALU pipes (Cody-Waite split + cubic), for a share of the softmax exponentials: the
+// MUFU unit evaluates 16 ex2 per clock and SM, and pass 2 of a key tile needs 16 384 per CTA - the pipe that
+// bounds this kernel. round(x) comes out of the magic-number add (1.5 * 2^23), the cubic covers
+// [-0.5, 0.5] with a relative error of 6e-4 (P is rounded to bf16, 2e-3, right after), and the integer part goes
+// into the exponent field with one shift and one add.
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.05550411f, 0.24022651f);
+  p = fmaf(p, f, 0.69314718f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -255,7 +274,9 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
-            const float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
+            // every third exponential on the FMA pipe (exp2_fma): MUFU and FMA then finish together
+            const float x1 = __uint_as_float(r[2 * i + 1]) * sc - mn;
+            const float p1 = (ATT_POLY && i % 3 != 2) ? exp2_fma(x1) : fast_exp2(x1);
             lsum += p0 + p1;
             pk[i] = pack_bf16x2(p0, p1);
           }

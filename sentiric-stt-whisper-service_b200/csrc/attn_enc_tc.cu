@@ -35,8 +35,12 @@ constexpr int ATT_THREADS = 320;       // warp 0: TMA, warp 1: TMEM + MMA issue,
 // over the scores it came from and double-buffered O instead: P V(j) then had to be issued BEFORE S(j+1) and sat
 // on the serial chain; 1.44 vs 1.37 ms per layer for 64 windows.)
 constexpr int TMEM_COLS = 256, TM_P = 128, TM_O = 192;
+// Measured and rejected (round 2, profiles/r2_attn_exp2_poly.txt): with every third exponential on the FMA pipe the
+// encoder went from 2.65 to 2.73 ms per window - pass 2 is bound by issue slots (ex2 + ffma + cvt + the tcgen05.ld/st
+// traffic of 256 softmax threads), not by the MUFU unit alone, and the nine extra FMA/ALU instructions per element
+// cost more than the ex2 they replace. Kept behind -DSW_ATT_POLY=1.
 #ifndef SW_ATT_POLY
-#define SW_ATT_POLY 1
+#define SW_ATT_POLY 0
 #endif
 constexpr bool ATT_POLY = SW_ATT_POLY != 0;
 

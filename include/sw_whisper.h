@@ -245,9 +245,19 @@ SW_API int sw_dev_gemm_bf16(const void* dA, const void* dB, void* dC, const floa
 SW_API int sw_dev_skinny_gemm(const void* dX, const void* dW, int R, int N, int K, const float* d_bias,
                               int gelu, void* d_out, float* d_partial, int split, void* stream);
 SW_API int sw_dev_skinny_split(int N, int K);
+/* the same with the kernel named: 0 = the engine's choice, 1 = mma.sync tiles (skinny_gemm.cu), 2 = tcgen05 with the
+   weight rows in the M dimension (skinny_gemm_tc.cu) */
+SW_API int sw_dev_skinny_gemm_k(int kernel, const void* dX, const void* dW, int R, int N, int K, const float* d_bias,
+                                int gelu, void* d_out, float* d_partial, int split, void* stream);
+SW_API int sw_dev_skinny_split_k(int kernel, int N, int K);
 SW_API int sw_dev_layer_norm(float* d_x, int rows, int d, const float* g, const float* b,
                              void* d_out_bf16, const float* d_partial, int n_split, const float* d_bias,
                              void* stream);
+/* development: hold n_ctas SMs (smem_bytes of shared memory and most of the register file each) for ms
+   milliseconds on a private stream, optionally streaming stream_bytes of HBM meanwhile; n_ctas <= 0 waits
+   for it to leave (tools/dev_chain_occupied.py: cost of a decoder layer's latency chain beside a resident
+   cross attention) */
+SW_API int sw_dev_occupy(int n_ctas, int smem_bytes, float ms, size_t stream_bytes);
 
 #ifdef __cplusplus
 }

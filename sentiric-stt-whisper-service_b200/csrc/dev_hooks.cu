@@ -4,7 +4,65 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 
+namespace {
+// Development occupier (tools/dev_chain_occupied.py): holds `gridDim.x` SMs (dynamic shared memory + a register
+// footprint that keeps other CTAs out, like a resident cross-attention CTA) for `ns` nanoseconds; `buf` != null:
+// additionally streams it (HBM contention). Measures what a decoder layer's latency chain costs on the SMs and the
+// HBM share a concurrent cross attention leaves it.
+__global__ void __launch_bounds__(512, 1) occupy_kernel(unsigned long long ns, const uint4* __restrict__ buf, size_t n_vec,
+                                                       float* sink) {
+  extern __shared__ uint8_t occ_smem[];
+  float r[96];
+#pragma unroll
+  for (int i = 0; i < 96; ++i) r[i] = (float)(threadIdx.x + i);
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  do {
+    if (buf) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint4 v = __ldcs(buf + (idx + u * stride) % n_vec);
+        acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+      }
+      idx += 8 * stride;
+    }
+#pragma unroll
+    for (int i = 0; i < 96; ++i) r[i] = fmaf(r[i], 1.0000001f, 1e-9f);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 96; ++i) s += r[i];
+  if (s == 12345.678f || (acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345u) sink[0] = s + occ_smem[threadIdx.x];
+}
+}  // namespace
+
 extern "C" {
+
+int sw_dev_occupy(int n_ctas, int smem_bytes, float ms, size_t stream_bytes) {
+  static cudaStream_t st = nullptr;
+  static uint4* buf = nullptr;
+  static size_t buf_bytes = 0;
+  static float* sink = nullptr;
+  if (!st) {
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return -1;
+    if (cudaMalloc(&sink, 16) != cudaSuccess) return -1;
+  }
+  if (n_ctas <= 0) return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1;  // wait for the occupier to leave
+  if (stream_bytes > buf_bytes) {
+    if (buf) cudaFree(buf);
+    if (cudaMalloc(&buf, stream_bytes) != cudaSuccess) return -1;
+    cudaMemsetAsync(buf, 1, stream_bytes, st);
+    buf_bytes = stream_bytes;
+  }
+  if (cudaFuncSetAttribute(occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return -1;
+  occupy_kernel<<<n_ctas, 512, smem_bytes, st>>>((unsigned long long)(ms * 1e6), stream_bytes ? buf : nullptr,
+                                                  stream_bytes / 16, sink);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
 
 int sw_device_count(void) {
   int n = 0;
@@ -49,6 +107,23 @@ int sw_dev_skinny_gemm(const void* dX, const void* dW, int R, int N, int K, cons
                          gelu, static_cast<sw::bf16*>(d_out), N, d_partial, split, static_cast<cudaStream_t>(stream));
 }
 int sw_dev_skinny_split(int N, int K) { return sw::skinny_split_for(N, K); }
+// kernel: 0 = what the engine would pick, 1 = mma.sync (skinny_gemm.cu), 2 = tcgen05 (skinny_gemm_tc.cu)
+int sw_dev_skinny_gemm_k(int kernel, const void* dX, const void* dW, int R, int N, int K, const float* d_bias, int gelu,
+                         void* d_out, float* d_partial, int split, void* stream) {
+  const sw::bf16* X = static_cast<const sw::bf16*>(dX);
+  const sw::bf16* W = static_cast<const sw::bf16*>(dW);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (kernel == 2) {
+    if (split <= 0) split = sw::skinny_tc_split_for(N, K);
+    return sw::skinny_gemm_tc(X, K, W, R, N, K, d_bias, gelu, static_cast<sw::bf16*>(d_out), N, d_partial, split, st);
+  }
+  if (split <= 0) split = kernel == 1 ? sw::skinny_mma_split_for(N, K) : sw::skinny_split_for(N, K);
+  return sw::skinny_gemm(X, K, W, R, N, K, d_bias, gelu, static_cast<sw::bf16*>(d_out), N, d_partial, split, st,
+                         kernel == 1 ? -1 : 0);
+}
+int sw_dev_skinny_split_k(int kernel, int N, int K) {
+  return kernel == 2 ? sw::skinny_tc_split_for(N, K) : kernel == 1 ? sw::skinny_mma_split_for(N, K) : sw::skinny_split_for(N, K);
+}
 int sw_dev_layer_norm(float* d_x, int rows, int d, const float* g, const float* b, void* d_out_bf16,
                       const float* d_partial, int n_split, const float* d_bias, void* stream) {
   return sw::layer_norm(d_x, rows, d, g, b, static_cast<sw::bf16*>(d_out_bf16), nullptr, d_partial, n_split,

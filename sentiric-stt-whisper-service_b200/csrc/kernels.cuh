@@ -132,6 +132,13 @@ int skinny_split_for(int N, int K);
 // resident cross-attention CTA)
 int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, const float* bias, int gelu,
                 bf16* out, int ldo, float* partial, int split, cudaStream_t stream, int stages = 0);
+// generation 3 (skinny_gemm_tc.cu): 128 weight rows per CTA in the M dimension of tcgen05.mma; skinny_gemm() and
+// skinny_split_for() route the wide models' matrices to it (skinny_use_tc)
+bool skinny_use_tc(int N, int K);
+int skinny_mma_split_for(int N, int K);  // the plan of the mma.sync kernel whatever skinny_use_tc says
+int skinny_tc_split_for(int N, int K);
+int skinny_gemm_tc(const bf16* X, int ldx, const bf16* W, int R, int N, int K, const float* bias, int gelu, bf16* out,
+                   int ldo, float* partial, int split, cudaStream_t stream);
 
 // ------------------------------------------------------------------ prosody (prosody.cu)
 // per-segment DSP of prosody_extractor.cpp:31-224 for all segments of an utterance

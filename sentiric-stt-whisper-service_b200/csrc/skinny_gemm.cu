@@ -201,7 +201,9 @@ int sk_pick_bn(int N, int K, int row_blocks, int split) {
 
 }  // namespace
 
-int skinny_split_for(int N, int K) {
+int skinny_split_for(int N, int K) { return skinny_use_tc(N, K) ? skinny_tc_split_for(N, K) : skinny_mma_split_for(N, K); }
+
+int skinny_mma_split_for(int N, int K) {
   // the K split (a divisor of the k-block count, slices of >= 2 k-blocks) that, with the better of the
   // two tile widths, leaves the fewest bytes on the most loaded SM; ties go to fewer splits
   const int n_kb = K / SK_BK;
@@ -221,6 +223,8 @@ int skinny_split_for(int N, int K) {
 int skinny_gemm(const bf16* X, int ldx, const bf16* W, int R, int N, int K, const float* bias, int gelu,
                 bf16* out, int ldo, float* partial, int split, cudaStream_t stream, int stages) {
   if (R <= 0) return 0;
+  if (stages >= 0 && skinny_use_tc(N, K))  // stages < 0: this kernel whatever the shape (development hook)
+    return skinny_gemm_tc(X, ldx, W, R, N, K, bias, gelu, out, ldo, partial, split, stream);
   SW_CHECK(K % SK_BK == 0 && ldx % 8 == 0 && N % 2 == 0, "skinny_gemm: unsupported shape N=%d K=%d ldx=%d", N, K, ldx);
   SW_CHECK(split >= 1 && split <= 32 && (split == 1 || partial), "skinny_gemm: split-K needs a partial buffer");
   SW_CHECK(K % (split * SK_BK) == 0, "skinny_gemm: K=%d not divisible into %d slices of 64-element blocks", K, split);

@@ -148,81 +148,54 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
     }
     if (item + (int)gridDim.x < n_items) prefetch_q(item + gridDim.x);
 
-    // Two 16-key stages per turn of the online-softmax recurrence (max -> alpha -> rescale O): the recurrence is a
-    // serial chain of ldmatrix -> mma -> shuffles -> ex2 -> mma per warp, and with one stage per turn an SM streamed
-    // 56-59 GB/s whatever the grid size (measured at 64 and 96 CTAs) - the chain, not HBM, bounded every launch that
-    // does not use all SMs. 32 keys per turn halve the number of turns; the two stages' Q K^T are independent.
-    for (int i = 0, ns = 0; i < n_st; i += 2, it += ns) {
-      ns = min(2, n_st - i);
-      const int s0 = it % n_stages, s1 = (it + 1) % n_stages;
-      mbar_wait(&full[s0], (it / n_stages) & 1);
-      if (ns == 2) mbar_wait(&full[s1], ((it + 1) / n_stages) & 1);
-      const uint32_t stg[2] = {sbase + s0 * stage_bytes, sbase + s1 * stage_bytes};
-      const int nk0 = min(XA_KEYS, key_end - key_begin - i * XA_KEYS);
-      const int nk1 = ns == 2 ? min(XA_KEYS, key_end - key_begin - (i + 1) * XA_KEYS) : 0;
-      uint32_t dep0 = 0, dep1 = 0;  // one result register of every ldmatrix of a stage (mbar_arrive_after_reads)
+    for (int i = 0; i < n_st; ++i, ++it) {
+      const int s = it % n_stages;
+      const uint32_t ph = (it / n_stages) & 1;
+      mbar_wait(&full[s], ph);
+      const uint32_t st = sbase + s * stage_bytes;
+      const int nk = min(XA_KEYS, key_end - key_begin - i * XA_KEYS);
+      uint32_t dep = 0;  // one result register of every ldmatrix of this stage (mbar_arrive_after_reads)
 #pragma unroll
       for (int hs = 0; hs < HPW; ++hs) {
         const int hl = warp + hs * n_cons;
         if (hl >= nh_cta) continue;
-        float sc[2][2][4];
+        const uint32_t kt = st + hl * 2048, vt = st + half_bytes + hl * 2048;  // [16 keys][128 B] swizzled tiles
+        float sc[2][4];
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+        for (int nt = 0; nt < 2; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt) sc[q][nt][0] = sc[q][nt][1] = sc[q][nt][2] = sc[q][nt][3] = 0.f;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (q < ns) {
-            const uint32_t kt = stg[q] + hl * 2048;  // [16 keys][128 B] swizzled tile
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              uint32_t b[4];
-              const int key = (lane & 7) + (lane >> 4) * 8;
-              const int ch = ks * 2 + ((lane >> 3) & 1);
-              ldmatrix_x4(b, kt + key * 128 + ((ch ^ (key & 7)) << 4));
-              if (q == 0) dep0 ^= b[0];
-              else dep1 ^= b[0];
-              const uint32_t b01[2] = {b[0], b[1]}, b23[2] = {b[2], b[3]};
-              mma_m16n8k16_bf16(sc[q][0], qa[hs][ks], b01);
-              mma_m16n8k16_bf16(sc[q][1], qa[hs][ks], b23);
-            }
-          }
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t b[4];
+          const int key = (lane & 7) + (lane >> 4) * 8;
+          const int ch = ks * 2 + ((lane >> 3) & 1);
+          ldmatrix_x4(b, kt + key * 128 + ((ch ^ (key & 7)) << 4));
+          dep ^= b[0];
+          const uint32_t b01[2] = {b[0], b[1]}, b23[2] = {b[2], b[3]};
+          mma_m16n8k16_bf16(sc[0], qa[hs][ks], b01);
+          mma_m16n8k16_bf16(sc[1], qa[hs][ks], b23);
         }
-        // row g8 (decoder), keys q*16 + nt*8 + 2*t4 + {0,1}
-        float v[2][4];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int nk = q == 0 ? nk0 : nk1;
-          v[q][0] = sc[q][0][0] * qs; v[q][1] = sc[q][0][1] * qs; v[q][2] = sc[q][1][0] * qs; v[q][3] = sc[q][1][1] * qs;
-          if (nk < XA_KEYS) {
-            if (2 * t4 >= nk) v[q][0] = -INFINITY;
-            if (2 * t4 + 1 >= nk) v[q][1] = -INFINITY;
-            if (8 + 2 * t4 >= nk) v[q][2] = -INFINITY;
-            if (8 + 2 * t4 + 1 >= nk) v[q][3] = -INFINITY;
-          }
+        // row g8 (decoder), keys nt*8 + 2*t4 + {0,1}
+        float v00 = sc[0][0] * qs, v01 = sc[0][1] * qs, v10 = sc[1][0] * qs, v11 = sc[1][1] * qs;
+        if (nk < XA_KEYS) {
+          if (2 * t4 >= nk) v00 = -INFINITY;
+          if (2 * t4 + 1 >= nk) v01 = -INFINITY;
+          if (8 + 2 * t4 >= nk) v10 = -INFINITY;
+          if (8 + 2 * t4 + 1 >= nk) v11 = -INFINITY;
         }
-        float rmax = fmaxf(fmaxf(fmaxf(v[0][0], v[0][1]), fmaxf(v[0][2], v[0][3])),
-                           fmaxf(fmaxf(v[1][0], v[1][1]), fmaxf(v[1][2], v[1][3])));
+        float rmax = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
         rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 1));
         rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 2));
         const float mn = fmaxf(m[hs], rmax);
         const float alpha = fast_exp2(m[hs] - mn);
-        float pr[2][4];
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) pr[q][c] = fast_exp2(v[q][c] - mn);
+        const float p00 = fast_exp2(v00 - mn), p01 = fast_exp2(v01 - mn);
+        const float p10 = fast_exp2(v10 - mn), p11 = fast_exp2(v11 - mn);
         m[hs] = mn;
-        l[hs] = l[hs] * alpha + ((pr[0][0] + pr[0][1]) + (pr[0][2] + pr[0][3])) +
-                ((pr[1][0] + pr[1][1]) + (pr[1][2] + pr[1][3]));  // per-thread partial; quad-reduced at the end
-        uint32_t pa[2][4];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          pa[q][0] = pack_bf16x2(pr[q][0], pr[q][1]);
-          pa[q][1] = 0u;
-          pa[q][2] = pack_bf16x2(pr[q][2], pr[q][3]);
-          pa[q][3] = 0u;
-        }
+        l[hs] = l[hs] * alpha + (p00 + p01) + (p10 + p11);  // per-thread partial; quad-reduced at the end
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(p00, p01);
+        pa[1] = 0u;
+        pa[2] = pack_bf16x2(p10, p11);
+        pa[3] = 0u;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
           o[hs][nt][0] *= alpha;
@@ -230,23 +203,16 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
         }
 #pragma unroll
         for (int dp = 0; dp < 4; ++dp) {
+          uint32_t b[4];
+          const int key = (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int ch = dp * 2 + (lane >> 4);
+          ldmatrix_x4_trans(b, vt + key * 128 + ((ch ^ (key & 7)) << 4));
+          dep ^= b[0];
+          const uint32_t b01[2] = {b[0], b[1]}, b23[2] = {b[2], b[3]};
           float acc0[4] = {o[hs][2 * dp][0], o[hs][2 * dp][1], 0.f, 0.f};
           float acc1[4] = {o[hs][2 * dp + 1][0], o[hs][2 * dp + 1][1], 0.f, 0.f};
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            if (q < ns) {
-              const uint32_t vt = stg[q] + half_bytes + hl * 2048;
-              uint32_t b[4];
-              const int key = (lane & 7) + ((lane >> 3) & 1) * 8;
-              const int ch = dp * 2 + (lane >> 4);
-              ldmatrix_x4_trans(b, vt + key * 128 + ((ch ^ (key & 7)) << 4));
-              if (q == 0) dep0 ^= b[0];
-              else dep1 ^= b[0];
-              const uint32_t b01[2] = {b[0], b[1]}, b23[2] = {b[2], b[3]};
-              mma_m16n8k16_bf16(acc0, pa[q], b01);
-              mma_m16n8k16_bf16(acc1, pa[q], b23);
-            }
-          }
+          mma_m16n8k16_bf16(acc0, pa, b01);
+          mma_m16n8k16_bf16(acc1, pa, b23);
           o[hs][2 * dp][0] = acc0[0];
           o[hs][2 * dp][1] = acc0[1];
           o[hs][2 * dp + 1][0] = acc1[0];
@@ -254,10 +220,7 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
         }
       }
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_after_reads(&empty[s0], dep0, zero);
-        if (ns == 2) mbar_arrive_after_reads(&empty[s1], dep1, zero);
-      }
+      if (lane == 0) mbar_arrive_after_reads(&empty[s], dep, zero);
     }
     // ---- partial result of this (window, chunk): unnormalised O, running max m and sum l per head
 #pragma unroll
@@ -369,12 +332,7 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
   // the ring 5 deep instead of 2 - with two stages an SM streamed 55 GB/s whatever the grid (64, 96 CTAs measured),
   // i.e. the ring, not HBM, bounded every capped launch. SW_XA_HSPLIT=1 restores whole windows per CTA (development).
   static const int force_hsplit = getenv("SW_XA_HSPLIT") ? atoi(getenv("SW_XA_HSPLIT")) : 0;
-  // ... and whenever a warp would otherwise own several heads (12 and 16 heads: one head per warp keeps the
-  // two-stage turn below in registers)
-  int full_cons = 1;
-  for (int c = 1; c <= XA_MAX_CONSUMERS; ++c)
-    if (n_head % c == 0) full_cons = c;
-  int n_hsplit = ((XA_KEYS * 2 * d * 2 * 3 > 220 * 1024 || n_head / full_cons > 1) && n_head % 2 == 0) ? 2 : 1;
+  int n_hsplit = (XA_KEYS * 2 * d * 2 * 3 > 220 * 1024 && n_head % 2 == 0) ? 2 : 1;
   if (force_hsplit == 1 || (force_hsplit == 2 && n_head % 2 == 0)) n_hsplit = force_hsplit;
   const int nh_cta = n_head / n_hsplit;
   // consumer warps: the largest divisor of the item's heads that is <= 10, so every warp owns the same number of heads

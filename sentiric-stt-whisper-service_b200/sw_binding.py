@@ -85,7 +85,8 @@ EXPORTS = [
     "sw_ctx_get_stats", "sw_ctx_set_kernel_timing", "sw_mel_pcm16", "sw_mel_f32", "sw_encode", "sw_decode_logits",
     "sw_prosody_default_opts", "sw_prosody_segments_f32", "sw_prosody_segments_pcm16",
     "sw_resample_out_len", "sw_resample_f32",
-    "sw_dev_gemm_bf16", "sw_dev_skinny_gemm", "sw_dev_skinny_split", "sw_dev_layer_norm"]
+    "sw_dev_gemm_bf16", "sw_dev_skinny_gemm", "sw_dev_skinny_split", "sw_dev_layer_norm", "sw_dev_occupy",
+    "sw_dev_skinny_gemm_k", "sw_dev_skinny_split_k"]
 
 _lib = None
 

@@ -89,26 +89,29 @@ SKINNY = [
 ]
 
 
+@pytest.mark.parametrize("kernel", [1, 2], ids=["mma_sync", "tcgen05"])
 @pytest.mark.parametrize("case", SKINNY, ids=lambda c: "R%d_N%d_K%d_s%d" % c[:4])
-def test_skinny_gemm_matches_fp32_reference(gemm_check, case):
-    """The decoder step's weight-streaming GEMM (skinny_gemm.cu) against torch fp32 on the same bf16 inputs:
-    bf16 out within one bf16 rounding of the range, split-K f32 partials summed within 1e-3 of the range."""
+def test_skinny_gemm_matches_fp32_reference(gemm_check, case, kernel):
+    """The decoder step's weight-streaming GEMMs (skinny_gemm.cu: mma.sync tiles; skinny_gemm_tc.cu: tcgen05 with the
+    weight rows in the M dimension) against torch fp32 on the same bf16 inputs: bf16 out within one bf16 rounding of
+    the range, split-K f32 partials summed within 1e-3 of the range; rows / partial slices the launch does not own
+    stay untouched."""
     import ctypes
     import torch
     R, N, K, split, bias, gelu = case
     lib = gemm_check.lib
     vp, ci = ctypes.c_void_p, ctypes.c_int
-    lib.sw_dev_skinny_gemm.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp, vp, ci, vp]
+    lib.sw_dev_skinny_gemm_k.argtypes = [ci, vp, vp, ci, ci, ci, vp, ci, vp, vp, ci, vp]
     g = torch.Generator(device="cuda").manual_seed(R + N + K)
     X = (torch.randn(R, K, device="cuda", generator=g) * 0.5).bfloat16()
     W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
     b = torch.randn(N, device="cuda", generator=g) if bias else None
-    sp = split if split > 0 else lib.sw_dev_skinny_split(N, K)
+    sp = split if split > 0 else lib.sw_dev_skinny_split_k(kernel, N, K)
     ref = X.float() @ W.float().t()
     if sp == 1:
-        out = torch.full((R, N), 7.0, device="cuda", dtype=torch.bfloat16)
-        rc = lib.sw_dev_skinny_gemm(X.data_ptr(), W.data_ptr(), R, N, K, b.data_ptr() if bias else None, gelu,
-                                    out.data_ptr(), None, 1, None)
+        out = torch.full((R + 1, N), 7.0, device="cuda", dtype=torch.bfloat16)
+        rc = lib.sw_dev_skinny_gemm_k(kernel, X.data_ptr(), W.data_ptr(), R, N, K, b.data_ptr() if bias else None, gelu,
+                                      out.data_ptr(), None, 1, None)
         assert rc == 0, lib.sw_last_error()
         torch.cuda.synchronize()
         if bias:
@@ -116,13 +119,37 @@ def test_skinny_gemm_matches_fp32_reference(gemm_check, case):
         if gelu:
             ref = torch.nn.functional.gelu(ref, approximate="tanh")
         tol = 1e-2
-        got = out.float()
+        assert (out[R] == 7.0).all()      # nothing written past the last row
+        got = out[:R].float()
     else:
-        part = torch.full((sp, R, N), 7.0, device="cuda")
-        rc = lib.sw_dev_skinny_gemm(X.data_ptr(), W.data_ptr(), R, N, K, None, 0, None, part.data_ptr(), sp, None)
+        part = torch.full((sp + 1, R, N), 7.0, device="cuda")
+        rc = lib.sw_dev_skinny_gemm_k(kernel, X.data_ptr(), W.data_ptr(), R, N, K, None, 0, None, part.data_ptr(), sp, None)
         assert rc == 0, lib.sw_last_error()
         torch.cuda.synchronize()
-        got = part.sum(0)
+        assert (part[sp] == 7.0).all()
+        got = part[:sp].sum(0)
         tol = 1e-3
     scale = max(1.0, ref.abs().max().item())
     assert (got - ref).abs().max().item() <= tol * scale
+
+
+def test_skinny_gemm_kernels_are_run_to_run_deterministic(gemm_check):
+    """Both decoder GEMM kernels give bit-identical results run to run (fixed summation order)."""
+    import ctypes
+    import torch
+    lib = gemm_check.lib
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    lib.sw_dev_skinny_gemm_k.argtypes = [ci, vp, vp, ci, ci, ci, vp, ci, vp, vp, ci, vp]
+    g = torch.Generator(device="cuda").manual_seed(11)
+    R, N, K = 64, 1280, 5120
+    X = (torch.randn(R, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    for kernel in (1, 2):
+        sp = lib.sw_dev_skinny_split_k(kernel, N, K)
+        outs = []
+        for _ in range(3):
+            part = torch.zeros(sp, R, N, device="cuda")
+            assert lib.sw_dev_skinny_gemm_k(kernel, X.data_ptr(), W.data_ptr(), R, N, K, None, 0, None, part.data_ptr(), sp, None) == 0
+            torch.cuda.synchronize()
+            outs.append(part)
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])

@@ -17,13 +17,17 @@ namespace sw {
 
 static void engine_free_step_graphs(Engine* e);
 
-// Programmatic dependent launch of the step kernels is OFF unless SW_PDL=1: measured inside the step
-// graph it costs 7 % (154.7 vs 144.1 us per layer, profiles/r1_step_kernel_costs_pdl_*.log) - early-resident
-// dependents take SM slots from the kernel they wait for, and a graph edge is already only ~1.5 us.
+// Programmatic dependent launch of the step kernels: ON unless SW_PDL=0. Round 1 measured it at -7 % inside the
+// step graph (154.7 vs 144.1 us per layer, profiles/r1_step_kernel_costs_pdl_*.log): the cross attention released
+// its dependents at its START, so the merge, the cross-out GEMM, ... became resident while it streamed for ~85 us
+// and held shared memory on the SMs the other lane's chain needs. Since round 2 the cross attention releases them
+// only when it ends, and the tcgen05 decoder GEMMs (skinny_gemm_tc.cu) occupy ~50 SMs each, so a dependent's
+// prologue and first weight tiles run on free SMs under its predecessor: chain of a layer on the 52 SMs a resident
+// cross attention leaves 72 -> 65 us, bench 3 761 -> 3 911 audio-s/s on the same box (profiles/r2_chain_occupied.txt).
 bool pdl_enabled() {
   static const bool on = [] {
     const char* p = getenv("SW_PDL");
-    return p && strcmp(p, "1") == 0;
+    return !(p && strcmp(p, "0") == 0);
   }();
   return on;
 }
@@ -154,7 +158,23 @@ Engine* engine_create_lane(const Engine* primary) {
   return e;
 }
 
-constexpr int XA_TIMED_EVERY = 8;
+// development: SW_XA_TRACE=1 brackets EVERY layer's cross attention and prints, for three steps, each launch's start
+// and end on a process-wide time axis (stderr) - the phase relation of the lanes' cache streams
+static bool xa_trace() {
+  static const bool on = getenv("SW_XA_TRACE") && atoi(getenv("SW_XA_TRACE")) != 0;
+  return on;
+}
+static const int XA_TIMED_EVERY = xa_trace() ? 1 : 8;
+static cudaEvent_t xa_trace_origin() {
+  static cudaEvent_t ev = [] {
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, 0);
+    cudaEventSynchronize(e);
+    return e;
+  }();
+  return ev;
+}
 
 #define GEMM(args)                                   \
   do {                                               \
@@ -517,6 +537,18 @@ int engine_decode_step(Engine* e, int R, int n_groups, int max_count, bool want_
       e->times.ms_xattn += t;
     }
     e->times.n_xattn += n_timed;
+    if (xa_trace() && e->times.n_steps >= 40 && e->times.n_steps < 43) {
+      float s0 = 0, s1 = 0;
+      cudaEventElapsedTime(&s0, xa_trace_origin(), e->ev0);
+      cudaEventElapsedTime(&s1, xa_trace_origin(), e->ev1);
+      fprintf(stderr, "XATRACE eng %p step %ld begin %.1f end %.1f us\n", (void*)e, e->times.n_steps, s0 * 1e3, s1 * 1e3);
+      for (int l = 0; l < L; ++l) {
+        float t0 = 0, t1 = 0;
+        cudaEventElapsedTime(&t0, xa_trace_origin(), e->xa_ev[2 * l]);
+        cudaEventElapsedTime(&t1, xa_trace_origin(), e->xa_ev[2 * l + 1]);
+        fprintf(stderr, "XATRACE eng %p step %ld layer %d xattn %.1f .. %.1f us\n", (void*)e, e->times.n_steps, l, t0 * 1e3, t1 * 1e3);
+      }
+    }
     // per launch: the cross-KV of every active window once + q in + attention out
     e->times.xattn_bytes += (double)n_timed * ((double)n_groups * 1500 * 2 * d * 2 + (double)R * d * 4);
   }

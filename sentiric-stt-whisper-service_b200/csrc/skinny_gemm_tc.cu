@@ -33,7 +33,7 @@ constexpr int ST_MAX_STAGES = 8;
 __global__ void __launch_bounds__(ST_THREADS, 1)
 skinny_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, int R, int N,
                       int k_slice, const float* __restrict__ bias, int gelu, bf16* __restrict__ out, int ldo,
-                      float* __restrict__ partial, int RB, int n_stages, int tmem_cols) {
+                      float* __restrict__ partial, int RB, int n_stages, int tmem_cols, int evict_last) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int stage_bytes = ST_W_BYTES + RB * ST_BK * 2;
@@ -71,9 +71,11 @@ skinny_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     if (elect_one_sync()) {
       // weights first (they do not depend on the predecessor), activations once it has finished
       const int pre = n_kb < n_stages ? n_kb : n_stages;
+      const uint64_t pol = l2_policy_evict_last();
       for (int kb = 0; kb < pre; ++kb) {
         mbar_arrive_expect_tx(&full[kb], stage_bytes);
-        tma_load_2d(smem + kb * stage_bytes, &map_w, &full[kb], k_begin + kb * ST_BK, n0);
+        if (evict_last) tma_load_2d_hint(smem + kb * stage_bytes, &map_w, &full[kb], k_begin + kb * ST_BK, n0, pol);
+        else tma_load_2d(smem + kb * stage_bytes, &map_w, &full[kb], k_begin + kb * ST_BK, n0);
       }
       pdl_wait();
       for (int kb = 0; kb < pre; ++kb)
@@ -83,7 +85,8 @@ skinny_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         mbar_wait(&empty[s], ((kb / n_stages) & 1) ^ 1);
         mbar_arrive_expect_tx(&full[s], stage_bytes);
         uint8_t* ws = smem + s * stage_bytes;
-        tma_load_2d(ws, &map_w, &full[s], k_begin + kb * ST_BK, n0);
+        if (evict_last) tma_load_2d_hint(ws, &map_w, &full[s], k_begin + kb * ST_BK, n0, pol);
+        else tma_load_2d(ws, &map_w, &full[s], k_begin + kb * ST_BK, n0);
         tma_load_2d(ws + ST_W_BYTES, &map_x, &full[s], k_begin + kb * ST_BK, r0);
       }
     }
@@ -193,9 +196,11 @@ int skinny_gemm_tc(const bf16* X, int ldx, const bf16* W, int R, int N, int K, c
   CUtensorMap map_w, map_x;
   if (make_tma_map_2d_bf16(&map_w, W, K, N, K, ST_BK, ST_BM)) return -1;
   if (make_tma_map_2d_bf16(&map_x, X, K, R, ldx, ST_BK, RB)) return -1;
+  // development switch: keep the weights in L2 for the other lane, which needs the same layer ~100 us later
+  static const int evict_last = getenv("SW_SKINNY_EVICT_LAST") ? atoi(getenv("SW_SKINNY_EVICT_LAST")) : 0;
   dim3 grid((N + ST_BM - 1) / ST_BM, split, row_blocks);
   SW_CUDA_CHECK(launch_pdl(skinny_gemm_tc_kernel, grid, dim3(ST_THREADS), smem, stream, map_w, map_x, R, N, k_slice, bias,
-                           gelu, out, ldo, partial, RB, n_stages, tmem_cols));
+                           gelu, out, ldo, partial, RB, n_stages, tmem_cols, evict_last));
   return 0;
 }
 

@@ -43,7 +43,8 @@ __global__ void __launch_bounds__((XA_MAX_CONSUMERS + 1) * 32, 1)
 cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* __restrict__ q,
                        const int* __restrict__ grp_win, const int* __restrict__ grp_start,
                        const int* __restrict__ grp_count, int T, int d, int n_head, int n_cons, int spc,
-                       int n_stages, int n_chunks, int n_items, float* __restrict__ ws, uint32_t zero, int n_hsplit) {
+                       int n_stages, int n_chunks, int n_items, float* __restrict__ ws, uint32_t zero, int n_hsplit,
+                       int evict_first) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -58,7 +59,9 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp: provably uniform
   const int row_f = d + 2 * n_head;  // floats per (row, chunk) partial
 
-  pdl_launch_dependents();
+  // No early launch_dependents here: the dependents (the merge, then the cross-out GEMM, ...) would become resident
+  // while this kernel streams for ~85 us and hold shared memory on exactly the SMs the OTHER lane's chain runs on.
+  // They are released when this CTA has nothing left to do (end of the kernel).
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_kv);
     for (int s = 0; s < n_stages; ++s) {
@@ -73,6 +76,7 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
     // no pdl_wait here: the cross-KV cache and the group tables were complete before the step's
     // first kernel started; the loads only fill this CTA's own shared memory
     if (elect_one_sync()) {  // not a lane test: one UTMALDG per load instead of a loop over the active lanes
+      const uint64_t pol = l2_policy_evict_first();
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int gc = item / n_hsplit, hh = item - gc * n_hsplit;
@@ -89,8 +93,13 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* _
           uint8_t* dst = smem + (size_t)s * stage_bytes;
           const int key = win * T + key_begin + i * XA_KEYS;
           // segments of the [K row | V row] cache line: K heads 0 .. n_head-1, then V heads
-          tma_load_3d(dst, &map_kv, &full[s], 0, key, hh * nh_cta);
-          tma_load_3d(dst + half_bytes, &map_kv, &full[s], 0, key, n_head + hh * nh_cta);
+          if (evict_first) {  // the cache is read once per step: do not let it push the lanes' shared weights out of L2
+            tma_load_3d_hint(dst, &map_kv, &full[s], 0, key, hh * nh_cta, pol);
+            tma_load_3d_hint(dst + half_bytes, &map_kv, &full[s], 0, key, n_head + hh * nh_cta, pol);
+          } else {
+            tma_load_3d(dst, &map_kv, &full[s], 0, key, hh * nh_cta);
+            tma_load_3d(dst + half_bytes, &map_kv, &full[s], 0, key, n_head + hh * nh_cta);
+          }
         }
       }
     }
@@ -312,6 +321,8 @@ void xa_plan(int n_groups, int T, int d, int max_ctas, int n_hsplit, int* spc_ou
   int ns = (220 * 1024) / stage_bytes;
   if (ns > 8) ns = 8;
   if (ns < 2) ns = 2;
+  static const int env_ns = getenv("SW_XA_STAGES") ? atoi(getenv("SW_XA_STAGES")) : 0;  // development switch
+  if (env_ns >= 2 && env_ns < ns) ns = env_ns;
   *n_stages = ns;
 }
 
@@ -355,6 +366,7 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
   const int box[3] = {64, XA_KEYS, nh_cta};
   if (make_tma_map_3d_bf16(&map, kv, dims, strides, box)) return -1;
   const int threads = (n_cons + 1) * 32;
+  static const int evict_first = getenv("SW_XA_EVICT") ? atoi(getenv("SW_XA_EVICT")) : 0;  // development switch
   // `ws` holds the partials of THIS call's rows (row0 .. row0 + R) from its start; the main kernel addresses rows
   // absolutely (through grp_start), so it gets the pointer moved back by row0 rows of n_chunks partials
   float* ws_main = ws - (int64_t)row0 * n_chunks * (d + 2 * n_head);
@@ -364,7 +376,7 @@ int cross_attention(const bf16* q, const bf16* kv, int64_t kv_rows, const int* d
     SW_CUDA_CHECK(opt_in.ensure(cross_attention_kernel<H>, (int)smem));                               \
     SW_CUDA_CHECK(launch_pdl(cross_attention_kernel<H>, dim3(grid), dim3(threads), smem, stream, map, \
                              q, d_grp_win, d_grp_start, d_grp_count, T, d, n_head, n_cons, spc,        \
-                             n_stages, n_chunks, n_items, ws_main, 0u, n_hsplit));                     \
+                             n_stages, n_chunks, n_items, ws_main, 0u, n_hsplit, evict_first));        \
   } while (0)
   switch (hpw) {
     case 1: XA_LAUNCH(1); break;

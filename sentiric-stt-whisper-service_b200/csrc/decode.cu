@@ -241,8 +241,10 @@ process_logits_kernel(const float* __restrict__ logits, int64_t ld, const LogitR
   const int n = cfg.n_vocab, beg = cfg.token_beg, tid = threadIdx.x;
   const float NEG = -INFINITY;
 
-  // pass 0: raw softmax statistics (no_speech_prob), masked copy into smem
-  float rmax = NEG;
+  // pass A: raw maximum (no_speech_prob), masked copy into smem, maxima of the masked text and timestamp logits
+  // (max_i fl(x_i - lse) == fl(max_i x_i - lse): the log-probability maxima of the timestamp-vs-text rule need no pass
+  // of their own)
+  float rmax = NEG, ts_raw = NEG, tx_raw = NEG;
   for (int i = tid; i < n; i += LP_THREADS) {
     const float raw = src[i];
     rmax = fmaxf(rmax, raw);
@@ -260,33 +262,28 @@ process_logits_kernel(const float* __restrict__ logits, int64_t ld, const LogitR
       }
     }
     if (i >= beg && i < beg + row.ts_min) sup = true;
-    lg[i] = sup ? NEG : v;
+    v = sup ? NEG : v;
+    lg[i] = v;
+    if (i >= beg) ts_raw = fmaxf(ts_raw, v);
+    else tx_raw = fmaxf(tx_raw, v);
   }
   rmax = block_max(rmax, red);
-  float rsum = 0.f;
-  for (int i = tid; i < n; i += LP_THREADS) rsum += expf(src[i] - rmax);
-  rsum = block_sum(rsum, red);
-  const float nosp = expf(src[cfg.token_nosp] - (logf(rsum) + rmax));
-
-  // log-softmax over the masked logits
-  float mx = NEG;
-  for (int i = tid; i < n; i += LP_THREADS) mx = fmaxf(mx, lg[i]);
-  mx = block_max(mx, red);
-  float se = 0.f;
-  for (int i = tid; i < n; i += LP_THREADS)
+  ts_raw = block_max(ts_raw, red);
+  tx_raw = block_max(tx_raw, red);
+  const float mx = fmaxf(ts_raw, tx_raw);
+  // pass B: both softmax denominators (raw: no_speech_prob; masked: log-softmax)
+  float rsum = 0.f, se = 0.f;
+  for (int i = tid; i < n; i += LP_THREADS) {
+    rsum += expf(src[i] - rmax);
     if (lg[i] > NEG) se += expf(lg[i] - mx);
+  }
+  rsum = block_sum(rsum, red);
   se = block_sum(se, red);
+  const float nosp = expf(src[cfg.token_nosp] - (logf(rsum) + rmax));
   const float lse = logf(se) + mx;
 
   // timestamp mass vs best text token
-  float ts_mx = NEG, tx_mx = NEG;
-  for (int i = tid; i < n; i += LP_THREADS) {
-    const float lp = lg[i] > NEG ? lg[i] - lse : NEG;
-    if (i >= beg) ts_mx = fmaxf(ts_mx, lp);
-    else tx_mx = fmaxf(tx_mx, lp);
-  }
-  ts_mx = block_max(ts_mx, red);
-  tx_mx = block_max(tx_mx, red);
+  const float ts_mx = ts_raw > NEG ? ts_raw - lse : NEG, tx_mx = tx_raw > NEG ? tx_raw - lse : NEG;
   float ts_se = 0.f;
   for (int i = beg + tid; i < n; i += LP_THREADS)
     if (lg[i] > NEG) ts_se += expf((lg[i] - lse) - ts_mx);
@@ -424,8 +421,7 @@ int process_logits_pick(const float* logits, int64_t ld, const LogitRow* d_rows,
   SW_CHECK(smem <= 210 * 1024, "process_logits: vocabulary of %d does not fit shared memory", cfg.n_vocab);
   SW_CUDA_CHECK(cudaFuncSetAttribute(process_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
-  process_logits_kernel<<<R, LP_THREADS, smem, stream>>>(logits, ld, d_rows, cfg, d_out);
-  SW_CUDA_CHECK(cudaGetLastError());
+  SW_CUDA_CHECK(launch_pdl(process_logits_kernel, dim3(R), dim3(LP_THREADS), smem, stream, logits, ld, d_rows, cfg, d_out));
   return 0;
 }
 

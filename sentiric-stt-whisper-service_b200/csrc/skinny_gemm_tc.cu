@@ -157,8 +157,9 @@ int tc_mode() {
 bool skinny_use_tc(int N, int K) {
   if (tc_mode() == 0 || K % ST_BK) return false;
   if (tc_mode() == 2) return true;
-  // wide models: with fewer than ~8 weight tiles per matrix there are not enough CTAs to stream from
-  return N >= 1024 && K >= 1024;
+  // small (d = 768) and wider: measured on BASELINE config 3 (small, beam 5) 9 654 -> 9 980 audio-s/s, config 2
+  // (base, d = 512) unchanged - below that a matrix has too few 128-row tiles to stream from
+  return N >= 768 && K >= 768;
 }
 
 // K split of the tcgen05 kernel: about 50 CTAs (weight tiles x slices) of >= 4 k-blocks each - as many as the SMs

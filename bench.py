@@ -421,16 +421,20 @@ def main():
         roofline=dict(bound="hbm", kernel="cross_attention_kernel", achieved=xa_gbs, peak=pk["hbm"],
                       unit="GB/s", frac=xa_gbs / pk["hbm"],
                       # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                      # (profiles/r1_ncu_xattn_v5.txt: 491.95 MB read = the algorithmic bytes, 20.1 MB of partials
+                      # (profiles/r2_ncu_xattn_v2.txt: 491.76 MB read = the algorithmic bytes, 5.1 MB of partials
                       # written; large-v3, 64 windows, one lane)
-                      traffic=512.0e6 if (args.model == "large-v3" and args.batch == 64) else None,
+                      traffic=496.9e6 if (args.model == "large-v3" and args.batch == 64) else None,
                       traffic_source="constant: dram bytes of one launch from the committed ncu --set full capture "
-                                     "(profiles/r1_ncu_xattn_v5.txt), not re-measured by this run",
+                                     "(profiles/r2_ncu_xattn_v2.txt), not re-measured by this run",
                       avg_launch_ms=xa_ms, algorithmic_bytes_per_launch=xa_bytes, peak_source=pk["src"],
-                      note=("timed with CUDA events on lane 0's stream while the other lane's kernels share the SMs and "
-                            "HBM (the grid is capped at 96 CTAs under lanes); alone on the GPU the same kernel runs at "
-                            "0.89 of peak (profiles/r1_bench_v10.json, r1_ncu_xattn_v5.txt). stages.decode_frac_of_hbm "
-                            "is the aggregate of both lanes.") if lanes > 1 else None),
+                      note=("timed with CUDA events on the lanes' streams inside the timed region. Under lanes the two "
+                            "lanes' cache streams alternate and, with programmatic dependent launch, overlap: a launch (96 "
+                            "CTAs) spends part of its elapsed time waiting for the SMs the other lane's stream still holds, so "
+                            "the per-launch durations of the two lanes add up to MORE than the wall time (profiles/"
+                            "r2_xattn_timeline.txt) and this fraction understates the kernel. `alone` is the same kernel timed "
+                            "the same way in a one-lane pass after the timed region (148 CTAs, nothing else on the GPU); "
+                            "stages.decode_frac_of_hbm is the aggregate of both lanes (all decode bytes / decode time).")
+                      if lanes > 1 else None),
         stages=dict(
             lanes=lanes,
             lanes_note="device_ms_per_step = per-lane device time summed over lanes / lanes (lanes overlap in time)",
@@ -514,6 +518,31 @@ def main():
                 sample="1 window with the reference's default n_threads = 4 (config.h:40), %.1f s" % dt4)
         o.close()
     eng.close()
+    if rank == 0 and world == 1 and lanes > 1 and xa_ms > 0:
+        # the dominant kernel with the GPU to itself: one lane (uncapped persistent grid), one pass of `batch`
+        # windows from pinned host buffers, outside every timed region
+        n1 = min(W, args.batch)
+        eng1 = swb.Engine(path, device=local_rank, max_batch=args.batch, max_beams=5, n_lanes=1)
+        eng1.set_kernel_timing(True)
+        p1 = eng1.default_params(1, beam_size=beam, **dict(SERVICE_PARAMS, language=langs[0])) if beam > 1 else \
+            eng1.default_params(0, **dict(SERVICE_PARAMS, language=langs[0]))
+        p1.n_threads = n_threads
+        for rep in range(2):
+            if rep == 1:
+                eng1.stats(reset=True)
+            for r in eng1.full_batch_ptrs(groups[0]["host"], groups[0]["lens"], n1, p1,
+                                          languages=groups[0]["langs"]):
+                L.sw_result_free(r)
+        s1 = eng1.stats(reset=True)
+        eng1.close()
+        if s1["n_xattn"] > 0 and s1["ms_xattn"] > 0:
+            ms1 = s1["ms_xattn"] / s1["n_xattn"]
+            b1 = s1["xattn_bytes"] / s1["n_xattn"]
+            line["roofline"]["alone"] = dict(
+                achieved=b1 / (ms1 * 1e-3) / 1e9, frac=b1 / (ms1 * 1e-3) / 1e9 / pk["hbm"], avg_launch_ms=ms1,
+                algorithmic_bytes_per_launch=b1, windows=n1,
+                decode_frac_of_hbm=s1["decode_bytes"] / (s1["ms_decode"] * 1e-3) / 1e9 / pk["hbm"],
+                note="one lane, %d windows, persistent grid on every SM; CUDA events on the lane's stream" % n1)
     if rank == 0 and world == 1 and args.facade:
         line["e2e_facade"] = run_facade(args, path, host_np, offs, n_samp, beam, langs[0])
     if rank == 0:

@@ -413,6 +413,32 @@ def test_beam_search_identical_on_keyed_model(keyed_tiny, ora):
         assert seg_ids(g) == gen_model.keyed_expected_tokens(info, synth_audio.keyed_symbols(k, s))
 
 
+def test_logit_kernel_cluster_sizes_agree(swb):
+    """process_logits shares a row of logits between the CTAs of a thread-block cluster whose size follows the number
+    of rows of the step (4 CTAs per row up to 37 rows, 2 up to 74, 1 above): the same clips must come back identical
+    whichever size served them - greedy, beam search (5 rows per window, inverse-CDF draws) and sampling at T = 0.4
+    (best_of 5), in batches of 4 / 10 / 16 windows = 20 / 50 / 80 beam rows."""
+    from tools import gen_model
+    path, info = model_file("tiny", script_len=40, keyed=4)
+    k = info["keyed"]
+    clips = [synth_audio.keyed_clip(k, synth_audio.keyed_symbols(k, s), seed=s) for s in range(700, 716)]
+    e = swb.Engine(path, max_batch=16, max_beams=5, n_lanes=1)
+    modes = [(0, dict(GREEDY)),
+             (1, dict(GREEDY, beam_size=5)),
+             (0, dict(language="en", temperature=0.4, temperature_inc=0.0, best_of=5, suppress_nst=1, token_timestamps=1))]
+    for strategy, kw in modes:
+        p = e.default_params(strategy, **kw)
+        by_n = {n: e.full_batch_pcm16(clips[:n], p) for n in (4, 10, 16)}
+        for i in range(16):
+            ref = by_n[16][i]
+            if kw.get("temperature", 0.0) == 0.0:
+                assert seg_ids(ref) == gen_model.keyed_expected_tokens(info, synth_audio.keyed_symbols(k, 700 + i))
+            for n in (4, 10):
+                if i < n:
+                    compare_results(by_n[n][i], ref, p_tol=1e-6)
+    e.close()
+
+
 def test_by_value_logit_config_is_not_baked_into_the_step_graph(swb, ora):
     """the decode step is replayed from a CUDA graph, and process_logits takes suppress_blank and the
     max_initial_ts bound BY VALUE - a later call with other values on the same context must not replay the old

@@ -164,7 +164,7 @@ static bool xa_trace() {
   static const bool on = getenv("SW_XA_TRACE") && atoi(getenv("SW_XA_TRACE")) != 0;
   return on;
 }
-static const int XA_TIMED_EVERY = xa_trace() ? 1 : 8;
+static const int XA_TIMED_EVERY = xa_trace() ? 1 : (getenv("SW_XA_TIMED_EVERY") ? std::max(1, atoi(getenv("SW_XA_TIMED_EVERY"))) : 8);
 static cudaEvent_t xa_trace_origin() {
   static cudaEvent_t ev = [] {
     cudaEvent_t e = nullptr;

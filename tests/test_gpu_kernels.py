@@ -84,6 +84,7 @@ SKINNY = [
     (64, 1280, 5120, 0, False, 0),    # FC2: K = 5120, split-K partials
     (7, 1280, 5120, 0, False, 0),     # a ragged row block
     (320, 3840, 1280, 1, True, 0),    # 64 windows x 5 beams: five row blocks
+    (64, 1000, 1280, 1, True, 0),     # a last weight tile that is not full
     (33, 384, 384, 0, False, 0),      # tiny widths
     (64, 1536, 384, 1, True, 1),
 ]

@@ -77,6 +77,13 @@ __device__ __forceinline__ float exp2_fma(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// LAGGED: the softmax of key tile j >= 1 is shifted by the running maximum of the tiles BEFORE it instead of its own
+// (any shift is a valid softmax shift as long as nothing overflows: P is a floating-point format, so its relative
+// precision does not depend on the shift), which removes the separate maximum pass - and the second tcgen05.ld of the
+// scores - from every tile but the first: the maximum of tile j is gathered inside the exponential pass and only
+// moves the shift of tile j + 1. A row whose tile maximum exceeds the shift by more than 2^60 recomputes its
+// probabilities with the new maximum (warp-uniform decision; both threads of a row take it together).
+template <bool LAGGED>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict__ out, int T, int d,
                             long long* __restrict__ trace) {  // trace: development timestamps (SW_ATTN_TRACE) or null
@@ -221,83 +228,105 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* _
     };
     const uint32_t s_addr = tmem + lane_addr + half * 64;
     const uint32_t p_addr = tmem + lane_addr + TM_P + half * 32;  // this thread's 64 probabilities: 32 packed columns
+    float shift_prev = 0.f;  // LAGGED: the shift the previous tile's probabilities were computed with
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = min(TK, T - j * TK);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       if (warp == 2 && lane == 0) ATT_TRACE(0, j, 0);
-      // ---- pass 1: maximum of this thread's 64 scores, then of the row
-      float mx = -INFINITY;
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(s_addr + cc * 32, r);
-        tmem_ld_wait(r);
-        if (c * 32 + 32 <= valid) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
-      }
-      // The partner's previous read of this slot happened before it arrived on p_ready for tile j-1, and
-      // S_j (whose completion we just waited for) was issued after all eight warps had arrived: no race.
-      // Exchanged as bf16 ROUNDED UP (any upper bound of the row maximum is a valid softmax shift, and both
-      // threads of the row must use the same one): 512 bytes instead of 1 KB keep two CTAs on an SM.
-      {
+      // the row maximum of this thread's 64 scores meets its partner's in shared memory. The partner's previous read
+      // of this slot happened before it arrived on p_ready for tile j-1, and S_j (whose completion we just waited
+      // for) was issued after all eight warps had arrived: no race. Exchanged as bf16 ROUNDED UP (both threads of
+      // the row must use the same value; 512 bytes instead of 1 KB keep two CTAs on an SM).
+      auto exchange_max = [&](float mx) {
         const uint32_t u = __float_as_uint(mx);
         uint32_t t = u & 0xffff0000u;
         if (t != u && !(u >> 31)) t += 0x10000u;
         mx = __uint_as_float(t);
         xch[half * 128 + row] = static_cast<uint16_t>(t >> 16);
-      }
-      if (warp == 2 && lane == 0) ATT_TRACE(0, j, 1);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (warp == 2 && lane == 0) ATT_TRACE(0, j, 2);
-      mx = fmaxf(mx, __uint_as_float(static_cast<uint32_t>(xch[(half ^ 1) * 128 + row]) << 16));
-      const float mn = fmaxf(m, mx * sc);
-      const float alpha = fast_exp2(m - mn);
-      m = mn;
-      if (j > 0) {  // P's columns are free once P V(j-1) has completed (it was queued a whole softmax ago)
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
-      }
-      // ---- pass 2: P = exp2(S * sc - m) -> bf16 -> tensor memory (the A operand of P V, TS form)
-      float lsum = 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        return fmaxf(mx, __uint_as_float(static_cast<uint32_t>(xch[(half ^ 1) * 128 + row]) << 16));
+      };
+      // one sweep over this thread's 64 scores: P = exp2(S * sc - shift) -> bf16 -> tensor memory (the A operand of
+      // P V, TS form); returns the row-sum share and the raw maximum of the scores
+      float lsum = 0.f, mx = -INFINITY;
+      auto sweep = [&](float shift, bool want_p) {
+        lsum = 0.f;
+        mx = -INFINITY;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(s_addr + cc * 32, r);
-        tmem_ld_wait(r);
-        uint32_t pk[16];
-        if (c * 32 + 32 <= valid) {  // full chunk: no masking
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = half * 2 + cc;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(s_addr + cc * 32, r);
+          tmem_ld_wait(r);
+          const bool full = c * 32 + 32 <= valid;
+          if (full) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
-            // every third exponential on the FMA pipe (exp2_fma): MUFU and FMA then finish together
-            const float x1 = __uint_as_float(r[2 * i + 1]) * sc - mn;
-            const float p1 = (ATT_POLY && i % 3 != 2) ? exp2_fma(x1) : fast_exp2(x1);
-            lsum += p0 + p1;
-            pk[i] = pack_bf16x2(p0, p1);
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
           }
-        } else {
+          if (!want_p) continue;
+          uint32_t pk[16];
+          if (full) {  // no masking
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - mn);
-            float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - mn);
-            if (c * 32 + 2 * i >= valid) p0 = 0.f;
-            if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
-            lsum += p0 + p1;
-            pk[i] = pack_bf16x2(p0, p1);
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - shift);
+              // every third exponential on the FMA pipe (exp2_fma): MUFU and FMA then finish together
+              const float x1 = __uint_as_float(r[2 * i + 1]) * sc - shift;
+              const float p1 = (ATT_POLY && i % 3 != 2) ? exp2_fma(x1) : fast_exp2(x1);
+              lsum += p0 + p1;
+              pk[i] = pack_bf16x2(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float p0 = fast_exp2(__uint_as_float(r[2 * i]) * sc - shift);
+              float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * sc - shift);
+              if (c * 32 + 2 * i >= valid) p0 = 0.f;
+              if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
+              lsum += p0 + p1;
+              pk[i] = pack_bf16x2(p0, p1);
+            }
           }
+          // P's columns are free once P V(j-1) has completed. It was queued behind S(j), whose completion started
+          // this sweep; by the time the first 32 probabilities exist it is long done, so the wait sits here and not in
+          // front of the sweep
+          if (cc == 0 && j > 0) {
+            mbar_wait(o_full, (j - 1) & 1);
+            tc_fence_after();
+          }
+          // 32 keys = 16 packed columns of this row, over scores this thread has already consumed
+          tmem_st_32x32b_x16(p_addr + cc * 16, pk);
         }
-        // 32 keys = 16 packed columns of this row, over scores this thread has already consumed
-        tmem_st_32x32b_x16(p_addr + cc * 16, pk);
+      };
+      float shift;  // of this tile's probabilities
+      if (!LAGGED || j == 0) {
+        // ---- two passes: the tile's own maximum first
+        sweep(0.f, false);
+        if (warp == 2 && lane == 0) ATT_TRACE(0, j, 1);
+        mx = exchange_max(mx);
+        if (warp == 2 && lane == 0) ATT_TRACE(0, j, 2);
+        m = fmaxf(m, mx * sc);
+        shift = m;
+        sweep(shift, true);
+      } else {
+        // ---- one pass, shifted by the maximum of the tiles before this one
+        shift = m;
+        sweep(shift, true);
+        if (warp == 2 && lane == 0) ATT_TRACE(0, j, 1);
+        mx = exchange_max(mx);
+        if (warp == 2 && lane == 0) ATT_TRACE(0, j, 2);
+        m = fmaxf(m, mx * sc);
+        if (__any_sync(0xffffffffu, m - shift > 60.f)) {  // the same 32 rows vote in both warps of a row
+          shift = m;
+          sweep(shift, true);
+        }
       }
+      const float alpha = j == 0 ? 1.f : fast_exp2(shift_prev - shift);
+      shift_prev = shift;
       l = l * alpha + lsum;  // this thread's half of the row sum (same alpha in both halves)
       if (warp == 2 && lane == 0) ATT_TRACE(0, j, 3);
       tmem_st_wait();
@@ -348,7 +377,14 @@ int encoder_attention_tc(const bf16* qkv, bf16* out, int n_win, int T, int d, in
   if (n_win <= 0) return 0;
   SW_CHECK(d == n_head * DH, "encoder_attention: head dim must be 64 (d=%d heads=%d)", d, n_head);
   static SmemOptIn opt_in;  // per device (host_common.h)
-  SW_CUDA_CHECK(opt_in.ensure(encoder_attention_tc_kernel, ATT_SMEM));
+  static SmemOptIn opt_in2;
+  SW_CUDA_CHECK(opt_in.ensure(encoder_attention_tc_kernel<true>, ATT_SMEM));
+  SW_CUDA_CHECK(opt_in2.ensure(encoder_attention_tc_kernel<false>, ATT_SMEM));
+  // development switch: SW_ATT_LAGGED=1 selects the one-pass softmax with the lagged shift. Measured (round 2, ABAB on
+  // one box, profiles/r2_attn_lagged_max.txt): parity green, encoder time unchanged (344.5 / 344.0 vs 344.4 / 349.6 ms
+  // per 128 windows) - removing the maximum pass does not shorten a key tile because the SM's two CTAs are bound by
+  // the exponentials they share, not by the instructions around them. The two-pass kernel stays the default.
+  static const bool lagged = getenv("SW_ATT_LAGGED") && atoi(getenv("SW_ATT_LAGGED")) == 1;
   CUtensorMap map;
   if (make_tma_map_2d_bf16(&map, qkv, 3 * (int64_t)d, (int64_t)n_win * T, 3 * (int64_t)d, 64, 128)) return -1;
   dim3 grid((T + TQ - 1) / TQ, n_head, n_win);
@@ -358,7 +394,8 @@ int encoder_attention_tc(const bf16* qkv, bf16* out, int n_win, int T, int d, in
     cudaMalloc(&d_trace, 2 * 16 * 8 * sizeof(long long));
     cudaMemset(d_trace, 0, 2 * 16 * 8 * sizeof(long long));
   }
-  encoder_attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(map, out, T, d, d_trace);
+  if (lagged) encoder_attention_tc_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(map, out, T, d, d_trace);
+  else encoder_attention_tc_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(map, out, T, d, d_trace);
   if (d_trace) {
     trace_left = 0;
     long long h[2 * 16 * 8];

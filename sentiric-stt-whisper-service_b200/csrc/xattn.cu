@@ -19,7 +19,8 @@
 // per launch instead of 79 + combine: the merging warp stalls the two-stage TMA pipeline of its CTA.)
 // The cache does not depend on the previous kernel of the step, so under programmatic dependent
 // launch the producer starts streaming it before griddepcontrol.wait; only the query load and the
-// stores wait.
+// stores wait. The kernel itself never calls launch_dependents: its successors (the merge, the cross-out
+// GEMM, ...) must not become resident while it streams (see the comment in the kernel).
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"

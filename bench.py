@@ -683,7 +683,7 @@ def run_facade(args, path, host_np, offs, n_samp, beam, lang):
     cli = os.path.join(PKG, "host", "build", "stt_cli")
     cmd = [cli, os.path.dirname(path), os.path.basename(path), raw, str(W), str(beam), "bench", "16000",
            "max_batch=%d" % args.batch, "steps=%d" % args.steps, "warmup=1", "clip=%d" % clip,
-           "language=%s" % lang, "batch_window_us=20000"]
+           "language=%s" % lang, "batch_window_us=20000", "admission=%d" % W]
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
         os.unlink(raw)

@@ -61,6 +61,7 @@ SttEngine::SttEngine(const Settings& settings) : settings_(settings) {
   free_slots_ = settings_.admission_slots > 0
                     ? settings_.admission_slots
                     : std::max(std::max(1, settings_.parallel_requests), 2 * std::max(1, settings_.max_batch));
+  capacity_ = free_slots_;
   // :44-52 - the reference loads a Silero model into whisper.cpp's CPU VAD. Not part of this build (see
   // set_vad_fn in the header): say so instead of silently running without the gate.
   if (settings_.enable_vad) {
@@ -98,12 +99,14 @@ void SttEngine::acquire_slot() {  // :63-79
                                     [this] { return free_slots_ > 0; });
   if (!ok) throw EngineBusyException("Server is busy (Queue timeout)");
   --free_slots_;
+  inside_.fetch_add(1, std::memory_order_relaxed);
 }
 
 void SttEngine::release_slot() {  // :81-85
   {
     std::lock_guard<std::mutex> lock(pool_mutex_);
     ++free_slots_;
+    inside_.fetch_sub(1, std::memory_order_relaxed);
   }
   pool_cv_.notify_one();
 }
@@ -118,9 +121,13 @@ void SttEngine::dispatcher_loop() {
       // a full device pass is max_batch windows on EVERY lane of the context (two lanes: 2 x max_batch)
       const int full_pass = settings_.max_batch * lanes_;
       if (settings_.batch_window_us > 0 && (int)queue_.size() < full_pass) {
-        // give concurrent callers a moment to join this device pass
-        q_cv_.wait_for(lk, std::chrono::microseconds(settings_.batch_window_us),
-                       [this, full_pass] { return stopping_ || (int)queue_.size() >= full_pass; });
+        // give concurrent callers a moment to join this device pass - unless nobody else CAN join: when every
+        // admission slot is taken and all of their holders already wait in this queue, no caller can arrive before
+        // a pass has run, and the rest of the window would be a pure loss
+        q_cv_.wait_for(lk, std::chrono::microseconds(settings_.batch_window_us), [this, full_pass] {
+          return stopping_ || (int)queue_.size() >= full_pass ||
+                 ((int)queue_.size() >= capacity_ && inside_.load(std::memory_order_relaxed) >= capacity_);
+        });
       }
       Request* head = queue_.front();
       queue_.pop_front();

@@ -5,6 +5,7 @@
 // single device pass - the reference runs one whisper_state per request and never batches
 // (stt_engine.cpp:36-42, 245).
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
@@ -114,6 +115,8 @@ class SttEngine {
   std::mutex pool_mutex_;
   std::condition_variable pool_cv_;
   int free_slots_ = 0;
+  int capacity_ = 0;             // admission slots in total
+  std::atomic<int> inside_{0};   // callers currently admitted
 
   // batching dispatcher
   std::mutex q_mutex_;
